@@ -1,0 +1,130 @@
+/*
+ * vmae.h — C ABI of libvmae_sm100a.so: hand-written sm_100a (B200) kernels for the video-MAE training step.
+ *
+ * The reference (lzc452/SSL-VIT-VIDEO-ANALYTICS) is pure PyTorch and has no FFI; each entry point below replaces the
+ * PyTorch op(s) cited next to it (paths relative to the reference root). INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (the library never allocates, frees or retains memory);
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and stream-ordered, no host sync inside;
+ *  - return value: 0 on success, negative on error (VMAE_ERR_*); vmae_last_error() gives the message (thread-local);
+ *  - there is no CPU or other-backend fallback: unsupported shapes fail with VMAE_ERR_UNSUPPORTED;
+ *  - bf16 tensors are raw uint16 storage (__nv_bfloat16); "ld*" are leading dimensions in ELEMENTS.
+ */
+#ifndef VMAE_H_
+#define VMAE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMAE_ABI_VERSION 1
+
+#define VMAE_ERR_BAD_ARG (-1)
+#define VMAE_ERR_UNSUPPORTED (-2)
+#define VMAE_ERR_CUDA (-3)
+#define VMAE_ERR_DRIVER (-4)
+
+#define VMAE_DTYPE_BF16 0
+#define VMAE_DTYPE_F32 1
+
+#define VMAE_MAJOR_K 0  /* contraction dimension contiguous: A is [M,K], B is [N,K] row-major */
+#define VMAE_MAJOR_MN 1 /* M/N dimension contiguous:        A is [K,M], B is [K,N] row-major */
+
+#define VMAE_ACT_NONE 0
+#define VMAE_ACT_GELU 1 /* exact erf GELU, as nn.GELU() / activation="gelu" in the reference */
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+const char* vmae_last_error(void);
+int vmae_abi_version(void);
+int vmae_device_sm_count(void);
+
+/* ---- K1: GEMM on tcgen05/TMEM, TMA-fed, fused epilogue ---------------------------------------------------------
+ * out[M,N] = epi( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulation.
+ *   epi(v) = ( act(v + bias[n]) * gelu'(aux_in[m,n]) ) + residual[m,n]     (each term optional)
+ *   aux_out (optional, with act=GELU) receives the pre-activation v + bias as bf16 (saved for backward).
+ *   accumulate=1 (fp32 out): out += epi(...) with red.add — used for split-K weight gradients into .grad.
+ * Replaces nn.Linear fwd/bwd: tiny_vit.py:79-81,93-94,105 ; mae_vit_adapter.py:24,40-53 ; tinyvit_mae.py:15,26.
+ * forward  : A = x (MAJOR_K),  B = W [N,K] (MAJOR_K)
+ * dgrad    : A = dy (MAJOR_K), B = W stored [N'=Kc, K'=N] (MAJOR_MN)
+ * wgrad    : A = dy stored [tokens=Kc, M] (MAJOR_MN), B = x stored [tokens=Kc, N] (MAJOR_MN), accumulate=1, k_splits>=1
+ */
+int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, int M, int N,
+                   int K, const float* bias, const float* residual, long long ld_res, const void* aux_in,
+                   long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out, long long ld_out,
+                   int out_dtype, int accumulate, int act, int k_splits, void* stream);
+
+/* ---- K2: flash attention on tcgen05/TMEM (non-causal, no mask, no dropout) --------------------------------------
+ * qkv: bf16 [B, L, 3, H, hd] (the packed projection output: q|k|v blocks, then head, then dim) — the layout of
+ * Attention.qkv (tiny_vit.py:93,100) and of nn.MultiheadAttention.in_proj (mae_vit_adapter.py:40-48).
+ * out: bf16 [B, L, H*hd]; lse: fp32 [B, H, L] (natural-log sum-exp of the scaled scores, saved for backward).
+ * Replaces F.scaled_dot_product_attention (tiny_vit.py:103) and the MHA core of nn.TransformerEncoderLayer.
+ */
+int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream);
+/* dqkv: bf16 [B, L, 3, H, hd]; delta: fp32 workspace [B, H, L] (rowsum(dO*O), written by the call). */
+int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                  int B, int L, int H, int hd, float scale, void* stream);
+
+/* ---- K3: LayerNorm (nn.LayerNorm eps=1e-5: tiny_vit.py:112,115; decoder norms mae_vit_adapter.py:40-50) ---------
+ * x: [rows, cols] fp32 or bf16 (x_dtype); y: bf16 or fp32 (y_dtype); mean/rstd: fp32 [rows] saved for backward. */
+int vmae_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                       float* mean, float* rstd, long long rows, int cols, float eps, void* stream);
+/* dx_out[r,:] = LN'(dy)[r,:] + (dx_resid ? dx_resid[r,:] : 0)   (fp32); optional bf16 copy of dx_out;
+ * dgamma/dbeta (fp32 [cols]) are ACCUMULATED into (red.add), matching autograd's .grad accumulation. */
+int vmae_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                       const float* rstd, const float* dx_resid, float* dx_out, void* dx_out_bf16, float* dgamma,
+                       float* dbeta, long long rows, int cols, void* stream);
+
+/* ---- K4: fused patchify + per-patch normalise + masked MSE (train_ssl_mae.py:26-31,72-84; mae/losses.py:19-41) --
+ * clip: fp32 [B,3,T,H,W]; tokens are (pt x ps x ps) tubelets, token order (t',h,w), element order (dt,py,px,c).
+ * pred: bf16 or fp32 [B, N, D], D = pt*ps*ps*3; mask: uint8 [B,N] (1 = masked).
+ * acc: fp32 [2] zero-initialised by the caller: acc[0] += sum over masked tokens of mean_e (pred-target)^2,
+ *      acc[1] += number of masked tokens.   loss = acc[0] / (acc[1] + 1e-6)  (vmae_masked_mse_finalize).
+ * diff (optional, bf16 [B,N,D]): pred - target on masked tokens, 0 on visible tokens (saved for backward).
+ * norm_pix: 0 = raw pixels, 1 = normalise with unbiased variance (torch.var default, train_ssl_mae.py:75),
+ *           2 = biased variance (mae/losses.py:37).  eps = 1e-6 inside the sqrt. */
+int vmae_masked_mse_fwd(const float* clip, const void* pred, int pred_dtype, const unsigned char* mask, float* acc,
+                        void* diff, int B, int T, int H, int W, int pt, int ps, int norm_pix, void* stream);
+/* loss[0] = acc[0]/(acc[1]+1e-6); scale[0] = 2/(D*(acc[1]+1e-6)) */
+int vmae_masked_mse_finalize(const float* acc, float* loss, float* scale, int D, void* stream);
+/* dpred = diff * scale[0] * gout[0]   (bf16 out, n elements) */
+int vmae_masked_mse_bwd(const void* diff, const float* scale, const float* gout, void* dpred, long long n, void* stream);
+
+/* ---- K5/K6: tube-mask index helpers, visible-tubelet gather, decoder-input scatter -------------------------------
+ * mask_frame: uint8 [B, L] (one frame of the tube mask, mae_loader.py:80-90); vis_idx: int32 [B, n_vis] ascending. */
+int vmae_mask_to_indices(const unsigned char* mask_frame, int* vis_idx, int B, int L, int n_vis, void* stream);
+/* im2col of the VISIBLE tubelets only: patches bf16 [B*Tp*n_vis, 3*pt*ps*ps] in Conv3d weight order (c,dt,py,px),
+ * row order (b, t', i); pos_rows (optional, fp32 [rows, D]) = temporal_pos[t'] + spatial_pos[vis_idx[b,i]]. */
+int vmae_gather_tubelets(const float* clip, const int* vis_idx, void* patches, const float* temporal_pos,
+                         const float* spatial_pos, float* pos_rows, int B, int T, int H, int W, int pt, int ps,
+                         int n_vis, int D, void* stream);
+/* decoder input (mae_vit_adapter.py:97-107): x_dec[b,t,l,:] = visible ? z[row(b,t,l),:] + tpos[t] + spos[l] : mask_token
+ * z: bf16 [B*Tp*n_vis, D] (vis_idx given) or bf16 [B*Tp*L, D] (vis_idx NULL: blend form); x_dec fp32 [B,Tp,L,D]. */
+int vmae_decoder_input_fwd(const void* z, const int* vis_idx, const unsigned char* mask, const float* temporal_pos,
+                           const float* spatial_pos, const float* mask_token, float* x_dec, int B, int Tp, int L,
+                           int n_vis, int D, void* stream);
+/* backward: dz (bf16, same shape as z; masked rows 0 in blend form), and ACCUMULATED fp32 dtpos[Tp,D], dspos[L,D],
+ * dmask_token[D]. */
+int vmae_decoder_input_bwd(const float* dx_dec, const int* vis_idx, const unsigned char* mask, void* dz, float* dtpos,
+                           float* dspos, float* dmask_token, int B, int Tp, int L, int n_vis, int D, void* stream);
+/* d(pos) of the encoder-side embedding: dtpos[t'] += rows, dspos[vis_idx[b,i]] += rows; dx fp32 [B*Tp*n_vis, D] */
+int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* dspos, int B, int Tp, int n_vis, int D,
+                      void* stream);
+
+/* ---- small memory-bound helpers -------------------------------------------------------------------------------- */
+int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+/* db[n] += sum_m dy[m,n]   (bias gradient; dy bf16 or fp32 [M, ld]) */
+int vmae_colsum_accum(const void* dy, int dy_dtype, long long ld, float* db, long long M, int N, void* stream);
+/* K8: z' = z + sigma * N(0,1) (privacy/feature_noise.py:4-7). Philox4x32-10 keyed by (seed, offset + element/4).
+ * eps_out (optional fp32) receives the unit normals that were drawn. In-place allowed (out == z). */
+int vmae_add_gaussian_noise(const void* z, void* out, int dtype, float* eps_out, long long n, float sigma,
+                            unsigned long long seed, unsigned long long offset, void* stream);
+/* K9 helper (FedAvg pre-scale, federated/fed_loop.py:45-49): y = alpha * x (+ y if accumulate), fp32 */
+int vmae_scale_f32(const float* x, float* y, float alpha, int accumulate, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMAE_H_ */
