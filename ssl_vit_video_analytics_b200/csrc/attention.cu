@@ -1,0 +1,562 @@
+// K2 — flash attention forward / backward on tcgen05 + TMEM (sm_100a), non-causal, no mask, no dropout.
+// Replaces F.scaled_dot_product_attention (tiny_vit.py:103) and the attention core of nn.TransformerEncoderLayer
+// (mae_vit_adapter.py:40-48). Input is the packed projection qkv[B, L, 3, H, hd]; q/k/v and the per-head slices are
+// addressed through TMA tensor-map coordinates, so no permute/contiguous copies are ever made.
+//
+// All three kernels share one skeleton: a CTA owns 128 rows (TMEM lanes); "score-like" tiles are produced by UMMA into
+// TMEM, four warps (one thread per row) turn them into bf16 operand tiles written to shared memory in the canonical
+// K-major 128B-swizzle layout, and a second UMMA consumes those tiles. Two CTAs are co-resident per SM so one CTA's
+// exp/elementwise phase overlaps the other's tensor-core phase.
+//
+//   forward : S = Q K^T -> online softmax -> P (smem) -> O_j = P V_j (TMEM) -> rescale-accumulate in registers
+//   dQ      : S = Q K^T, dP = dO V^T -> dS = P*(dP - delta)*scale (smem) -> dQ += dS K          (TMEM accumulate)
+//   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem) -> dV += P^T dO, dK += dS^T Q      (TMEM accumulate)
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/vmae.h"
+
+namespace vmae {
+
+constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 UMMA, warps 2..5 one thread per row
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Write 32 consecutive columns [col0, col0+32) of row r (as bf16) into a 128-row K-major SWIZZLE_128B operand tile:
+// 64-column chunks of 128 rows x 128 B; inside a row the 16-byte piece index is XORed with (r & 7).
+__device__ __forceinline__ void store_tile_row32(uint32_t tile, int r, int col0, const float (&v)[32]) {
+  const uint32_t row_base = tile + (col0 >> 6) * (128 * 128) + r * 128;
+  const int piece0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t addr = row_base + (((piece0 + i) ^ (r & 7)) << 4);
+    st_shared_v4(addr, pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+__device__ __forceinline__ void check_smem_alignment(const void* p) {
+  if (threadIdx.x == 0 && (smem_u32(p) & 1023u) != 0) {
+    printf("vmae attention: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+}
+
+// ======================================================================================================================
+// forward
+// ======================================================================================================================
+template <int HD, int BKV>
+struct FwdCfg {
+  static constexpr int ROWB = HD * 2;  // bytes per operand row == swizzle width (64 or 128)
+  static constexpr int Q_BYTES = 128 * ROWB;
+  static constexpr int KV_BYTES = BKV * ROWB;
+  static constexpr int P_BYTES = 128 * BKV * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;           // K[2]
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;      // V[2]
+  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int TMEM_COLS = (BKV + HD <= 128) ? 128 : 256;
+};
+
+template <int HD, int BKV>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale) {
+  using Cfg = FwdCfg<HD, BKV>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  check_smem_alignment(smem_raw);
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sQ = sbase + Cfg::OFF_Q, sP = sbase + Cfg::OFF_P;
+  auto sK = [&](int s) { return sbase + Cfg::OFF_K + s * Cfg::KV_BYTES; };
+  auto sV = [&](int s) { return sbase + Cfg::OFF_V + s * Cfg::KV_BYTES; };
+  const uint32_t bar = sbase + Cfg::OFF_BAR;
+  const uint32_t q_full = bar, s_full = bar + 8, p_ready = bar + 16, o_full = bar + 24;
+  auto kv_full = [&](int s) { return bar + 32 + 8 * s; };
+  auto kv_empty = [&](int s) { return bar + 48 + 8 * s; };
+  const uint32_t tmem_ptr_addr = bar + 64;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (L + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tS = tmem, tO = tmem + BKV;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      tma_load_3d(sQ, &map_q, q_full, h * HD, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(kv_full(s), 2 * Cfg::KV_BYTES);
+        tma_load_3d(sK(s), &map_kv, kv_full(s), (H + h) * HD, j * BKV, b);
+        tma_load_3d(sV(s), &map_kv, kv_full(s), (2 * H + h) * HD, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_full(s), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
+                    umma_smem_desc(sK(s) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_bf16(tO, umma_smem_desc(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
+                    umma_smem_desc(sV(s) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_o, kk > 0);
+        umma_commit(o_full);
+        umma_commit(kv_empty(s));
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float sl2 = scale * LOG2E;
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int valid = min(BKV, L - j * BKV);
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float alpha = exp2f((m - mx) * sl2);
+      m = mx;
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + lane_off + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+        }
+      }
+      l *= alpha;
+      const float msl = m * sl2;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + c * 32, r);
+        tmem_wait_ld();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          p[i] = (c * 32 + i < valid) ? exp2f(__uint_as_float(r[i]) * sl2 - msl) : 0.f;
+          l += p[i];
+        }
+        store_tile_row32(sP, row, c * 32, p);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q_row = q0 + row;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_off + c * 32, r);
+      tmem_wait_ld();
+      if (q_row < L) {
+        __nv_bfloat16* dst = out + (static_cast<long long>(b) * L + q_row) * (H * HD) + h * HD + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2((o[c * 32 + i] + __uint_as_float(r[i])) * inv_l, (o[c * 32 + i + 1] + __uint_as_float(r[i + 1])) * inv_l);
+          pk.y = pack_bf16x2((o[c * 32 + i + 2] + __uint_as_float(r[i + 2])) * inv_l, (o[c * 32 + i + 3] + __uint_as_float(r[i + 3])) * inv_l);
+          pk.z = pack_bf16x2((o[c * 32 + i + 4] + __uint_as_float(r[i + 4])) * inv_l, (o[c * 32 + i + 5] + __uint_as_float(r[i + 5])) * inv_l);
+          pk.w = pack_bf16x2((o[c * 32 + i + 6] + __uint_as_float(r[i + 6])) * inv_l, (o[c * 32 + i + 7] + __uint_as_float(r[i + 7])) * inv_l);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
+      }
+    }
+    if (q_row < L) lse[(static_cast<long long>(b) * H + h) * L + q_row] = m * scale + __logf(l);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
+}
+
+// ======================================================================================================================
+// backward: delta = rowsum(dO * O), then one templated kernel in two modes.
+// ======================================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int L, int H) {
+  const long long total = static_cast<long long>(B) * L * H;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int hh = static_cast<int>(idx % H);
+    const long long bl = idx / H;
+    const int ll = static_cast<int>(bl % L);
+    const int bb = static_cast<int>(bl / L);
+    const uint4* po = reinterpret_cast<const uint4*>(o + idx * HD);
+    const uint4* pd = reinterpret_cast<const uint4*>(dout + idx * HD);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 fa = __bfloat1622float2(a2[t]), fd = __bfloat1622float2(d2[t]);
+        acc += fa.x * fd.x + fa.y * fd.y;
+      }
+    }
+    delta[(static_cast<long long>(bb) * H + hh) * L + ll] = acc;
+  }
+}
+
+constexpr int BWD_DQ = 0;
+constexpr int BWD_DKDV = 1;
+
+template <int HD, int BS, int MODE>
+struct BwdCfg {
+  static constexpr int ROWB = HD * 2;
+  static constexpr int R_BYTES = 128 * ROWB;   // resident tile
+  static constexpr int Y_BYTES = BS * ROWB;    // streamed tile
+  static constexpr int E_BYTES = 128 * BS * 2; // bf16 operand tile written by the row threads
+  static constexpr int NUM_E = (MODE == BWD_DKDV) ? 2 : 1;
+  static constexpr int OFF_R0 = 0;
+  static constexpr int OFF_R1 = OFF_R0 + R_BYTES;
+  static constexpr int OFF_Y = OFF_R1 + R_BYTES;           // [2 stages][2 tiles]
+  static constexpr int OFF_E = OFF_Y + 4 * Y_BYTES;        // [NUM_E]
+  static constexpr int OFF_STAT = OFF_E + NUM_E * E_BYTES; // [2][2][BS] floats (DKDV only)
+  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * BS * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int TMEM_NEED = 2 * BS + NUM_E * HD;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+};
+
+// map_res_* have 128-row boxes (resident tiles), map_str_* have BS-row boxes (streamed tiles).
+template <int HD, int BS, int MODE>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_constant__ CUtensorMap map_str_qkv,
+                const __grid_constant__ CUtensorMap map_res_do, const __grid_constant__ CUtensorMap map_str_do,
+                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int H,
+                float scale) {
+  using Cfg = BwdCfg<HD, BS, MODE>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  check_smem_alignment(smem_raw);
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sR0 = sbase + Cfg::OFF_R0, sR1 = sbase + Cfg::OFF_R1;
+  auto sY = [&](int s, int t) { return sbase + Cfg::OFF_Y + (s * 2 + t) * Cfg::Y_BYTES; };
+  auto sE = [&](int t) { return sbase + Cfg::OFF_E + t * Cfg::E_BYTES; };
+  float* stat = reinterpret_cast<float*>(smem_raw + Cfg::OFF_STAT);
+  const uint32_t bar = sbase + Cfg::OFF_BAR;
+  const uint32_t res_full = bar, t_full = bar + 8, e_ready = bar + 16, e_free = bar + 24, acc_full = bar + 32;
+  auto st_full = [&](int s) { return bar + 40 + 8 * s; };
+  auto st_empty = [&](int s) { return bar + 56 + 8 * s; };
+  const uint32_t tmem_ptr_addr = bar + 72;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int niter = (L + BS - 1) / BS;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_res_qkv);
+    tma_prefetch_desc(&map_str_qkv);
+    tma_prefetch_desc(&map_res_do);
+    tma_prefetch_desc(&map_str_do);
+    mbar_init(res_full, 1);
+    mbar_init(t_full, 1);
+    mbar_init(e_ready, 128);
+    mbar_init(e_free, 1);
+    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tT0 = tmem, tT1 = tmem + BS, tA0 = tmem + 2 * BS, tA1 = tmem + 2 * BS + HD;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(res_full, 2 * Cfg::R_BYTES);
+      if (MODE == BWD_DQ) {
+        tma_load_3d(sR0, &map_res_qkv, res_full, h * HD, r0, b);          // Q
+        tma_load_3d(sR1, &map_res_do, res_full, h * HD, r0, b);           // dO
+      } else {
+        tma_load_3d(sR0, &map_res_qkv, res_full, (H + h) * HD, r0, b);    // K
+        tma_load_3d(sR1, &map_res_qkv, res_full, (2 * H + h) * HD, r0, b);// V
+      }
+      for (int it = 0; it < niter; ++it) {
+        const int s = it & 1;
+        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1u);
+        mbar_expect_tx(st_full(s), 2 * Cfg::Y_BYTES);
+        if (MODE == BWD_DQ) {
+          tma_load_3d(sY(s, 0), &map_str_qkv, st_full(s), (H + h) * HD, it * BS, b);      // K_j
+          tma_load_3d(sY(s, 1), &map_str_qkv, st_full(s), (2 * H + h) * HD, it * BS, b);  // V_j
+        } else {
+          tma_load_3d(sY(s, 0), &map_str_qkv, st_full(s), h * HD, it * BS, b);            // Q_i
+          tma_load_3d(sY(s, 1), &map_str_do, st_full(s), h * HD, it * BS, b);             // dO_i
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, BS, 0, 0);
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);
+      mbar_wait(res_full, 0);
+      for (int it = 0; it < niter; ++it) {
+        const int s = it & 1;
+        mbar_wait(st_full(s), (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          umma_bf16(tT0, umma_smem_desc(sR0 + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
+                    umma_smem_desc(sY(s, 0) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_t, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          umma_bf16(tT1, umma_smem_desc(sR1 + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
+                    umma_smem_desc(sY(s, 1) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_t, k > 0);
+        }
+        umma_commit(t_full);
+        mbar_wait(e_ready, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BS / 16; ++kk) {
+          // ACC0 += E0 * Y0 (Y0 read as an MN-major B operand: rows = contraction index, hd contiguous)
+          umma_bf16(tA0, umma_smem_desc(sE(0) + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
+                    umma_smem_desc(sY(s, 0) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_a, (it > 0 || kk > 0));
+        }
+        if (MODE == BWD_DKDV) {
+#pragma unroll
+          for (int kk = 0; kk < BS / 16; ++kk) {
+            umma_bf16(tA1, umma_smem_desc(sE(1) + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
+                      umma_smem_desc(sY(s, 1) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_a, (it > 0 || kk > 0));
+          }
+        }
+        umma_commit(st_empty(s));
+        umma_commit(e_free);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int tid = threadIdx.x - 64;  // 0..127 among the row threads
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float sl2 = scale * LOG2E;
+    const int g_row = r0 + row;
+    const long long stat_base = (static_cast<long long>(b) * H + h) * L;
+    float lse_row = 0.f, delta_row = 0.f;
+    if (MODE == BWD_DQ && g_row < L) {
+      lse_row = lse[stat_base + g_row] * LOG2E;
+      delta_row = delta[stat_base + g_row];
+    }
+    for (int it = 0; it < niter; ++it) {
+      const int valid = min(BS, L - it * BS);
+      float* st_lse = stat + (it & 1) * 2 * BS;
+      float* st_delta = st_lse + BS;
+      if (MODE == BWD_DKDV) {
+        // column statistics of the streamed query block
+        for (int i = tid; i < 2 * BS; i += 128) {
+          const int c = i % BS;
+          const int g = it * BS + c;
+          float v = 0.f;
+          if (g < L) v = (i < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
+          st_lse[i] = v;  // st_delta == st_lse + BS
+        }
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(t_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(e_free, (it - 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c < BS / 32; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tT0 + lane_off + c * 32, rs);
+        tmem_ld32(tT1 + lane_off + c * 32, rp);
+        tmem_wait_ld();
+        float ds[32], pp[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i;
+          float p;
+          if (MODE == BWD_DQ) {
+            p = (col < valid) ? exp2f(__uint_as_float(rs[i]) * sl2 - lse_row) : 0.f;
+            ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+          } else {
+            p = (col < valid) ? exp2f(__uint_as_float(rs[i]) * sl2 - st_lse[col]) : 0.f;
+            ds[i] = p * (__uint_as_float(rp[i]) - st_delta[col]) * scale;
+            pp[i] = p;
+          }
+        }
+        store_tile_row32(sE(0), row, c * 32, ds);
+        if (MODE == BWD_DKDV) store_tile_row32(sE(1), row, c * 32, pp);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(e_ready);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    // write the accumulators: DQ -> q slot; DKDV -> k slot (ACC0) and v slot (ACC1)
+    const long long row_off = (static_cast<long long>(b) * L + g_row) * (3 * H * HD);
+#pragma unroll
+    for (int a = 0; a < Cfg::NUM_E; ++a) {
+      const int part = (MODE == BWD_DQ) ? 0 : (a == 0 ? 1 : 2);
+      const uint32_t tA = (a == 0) ? tA0 : tA1;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tA + lane_off + c * 32, r);
+        tmem_wait_ld();
+        if (g_row < L) {
+          __nv_bfloat16* dst = dqkv + row_off + (part * H + h) * HD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            *reinterpret_cast<uint4*>(dst + i) = pk;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
+}
+
+static int make_map_rows(CUtensorMap* m, const void* base, int B, int L, int width, int hd, int box_rows) {
+  const uint64_t dims[3] = {(uint64_t)width, (uint64_t)L, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)width * 2, (uint64_t)L * width * 2};
+  const uint32_t box[3] = {(uint32_t)hd, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(m, base, 3, dims, str, box, hd * 2);
+}
+
+template <int HD, int BKV>
+static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t stream) {
+  using Cfg = FwdCfg<HD, BKV>;
+  CUtensorMap mq, mkv;
+  int rc = make_map_rows(&mq, qkv, B, L, 3 * H * HD, HD, 128);
+  if (rc) return rc;
+  rc = make_map_rows(&mkv, qkv, B, L, 3 * H * HD, HD, BKV);
+  if (rc) return rc;
+  auto kern = attn_fwd_kernel<HD, BKV>;
+  VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((L + 127) / 128, H, B);
+  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+template <int HD, int BS, int MODE>
+static int launch_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int L, int H,
+                      float scale, cudaStream_t stream) {
+  using Cfg = BwdCfg<HD, BS, MODE>;
+  CUtensorMap m_res_qkv, m_str_qkv, m_res_do, m_str_do;
+  int rc = make_map_rows(&m_res_qkv, qkv, B, L, 3 * H * HD, HD, 128);
+  if (rc) return rc;
+  rc = make_map_rows(&m_str_qkv, qkv, B, L, 3 * H * HD, HD, BS);
+  if (rc) return rc;
+  rc = make_map_rows(&m_res_do, dout, B, L, H * HD, HD, 128);
+  if (rc) return rc;
+  rc = make_map_rows(&m_str_do, dout, B, L, H * HD, HD, BS);
+  if (rc) return rc;
+  auto kern = attn_bwd_kernel<HD, BS, MODE>;
+  VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((L + 127) / 128, H, B);
+  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H, scale);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+}  // namespace vmae
+
+using namespace vmae;
+
+extern "C" int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream) {
+  VMAE_CHECK_ARG(qkv && out && lse, "vmae_attn_fwd: null pointer");
+  VMAE_CHECK_ARG(B > 0 && L > 0 && H > 0, "vmae_attn_fwd: bad shape B=%d L=%d H=%d", B, L, H);
+  VMAE_CHECK_ARG(B <= 65535 && H <= 65535, "vmae_attn_fwd: B and H must be <= 65535");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (hd == 64) return launch_fwd<64, 128>(qkv, out, lse, B, L, H, scale, s);
+  if (hd == 32) return launch_fwd<32, 128>(qkv, out, lse, B, L, H, scale, s);
+  return fail(VMAE_ERR_UNSUPPORTED, "vmae_attn_fwd: head_dim %d unsupported (32 or 64)", hd);
+}
+
+extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
+                             int L, int H, int hd, float scale, void* stream) {
+  VMAE_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vmae_attn_bwd: null pointer");
+  VMAE_CHECK_ARG(B > 0 && L > 0 && H > 0, "vmae_attn_bwd: bad shape B=%d L=%d H=%d", B, L, H);
+  VMAE_CHECK_ARG(B <= 65535 && H <= 65535, "vmae_attn_bwd: B and H must be <= 65535");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)B * L * H;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  int rc;
+  if (hd == 64) {
+    attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
+    VMAE_LAUNCH_CHECK();
+    rc = launch_bwd<64, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    if (rc) return rc;
+    return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+  }
+  if (hd == 32) {
+    attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
+    VMAE_LAUNCH_CHECK();
+    rc = launch_bwd<32, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    if (rc) return rc;
+    return launch_bwd<32, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+  }
+  return fail(VMAE_ERR_UNSUPPORTED, "vmae_attn_bwd: head_dim %d unsupported (32 or 64)", hd);
+}

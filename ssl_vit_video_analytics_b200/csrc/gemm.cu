@@ -385,24 +385,24 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)lda * 2};
     const uint32_t box[2] = {64, (uint32_t)GEMM_BLOCK_M};
-    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, true);
+    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, 128);
   } else {
     const uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};
     const uint64_t str[1] = {(uint64_t)lda * 2};
     const uint32_t box[2] = {64, 64};
-    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, true);
+    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, 128);
   }
   if (rc) return rc;
   if (b_major == VMAE_MAJOR_K) {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)ldb * 2};
     const uint32_t box[2] = {64, (uint32_t)block_n};
-    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, true);
+    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
   } else {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
     const uint64_t str[1] = {(uint64_t)ldb * 2};
     const uint32_t box[2] = {64, 64};
-    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, true);
+    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
   }
   if (rc) return rc;
 

@@ -182,6 +182,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;                             // [61,64) layout = SWIZZLE_128B
   return d;
 }
+// Same with a runtime-selectable swizzle width: swz_bytes = 128 (layout 2) or 64 (layout 4).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swz_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(swz_bytes == 128 ? 2 : (swz_bytes == 64 ? 4 : 6)) << 61;
+  return d;
+}
+// named barrier among a subset of warps
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate. a_mn/b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
   return (1u << 4)            // c_format = F32
