@@ -115,6 +115,8 @@ int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* 
 /* ---- small memory-bound helpers -------------------------------------------------------------------------------- */
 int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+/* out = dy * gelu'(pre) (exact erf GELU, nn.GELU()); bf16, n elements (n % 8 == 0) */
+int vmae_gelu_bwd(const void* dy, const void* pre, void* out, long long n, void* stream);
 /* db[n] += sum_m dy[m,n]   (bias gradient; dy bf16 or fp32 [M, ld]) */
 int vmae_colsum_accum(const void* dy, int dy_dtype, long long ld, float* db, long long M, int N, void* stream);
 /* K8: z' = z + sigma * N(0,1) (privacy/feature_noise.py:4-7). Philox4x32-10 keyed by (seed, offset + element/4).

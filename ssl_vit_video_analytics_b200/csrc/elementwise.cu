@@ -223,8 +223,31 @@ __global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bf
 __global__ void __launch_bounds__(EW_THREADS) scale_f32_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, int accumulate, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = alpha * x[i];
-    y[i] = accumulate ? y[i] + v : v;
+    // separate IEEE multiply and add (no FMA contraction): bit-identical to the reference's CPU `acc += t * w`
+    const float v = __fmul_rn(alpha, x[i]);
+    y[i] = accumulate ? __fadd_rn(y[i], v) : v;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
+                                                              __nv_bfloat16* __restrict__ out, long long n) {
+  const long long n4 = n / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 d = load4<__nv_bfloat16>(dy + 4 * i);
+    const float4 h = load4<__nv_bfloat16>(pre + 4 * i);
+    float4 o;
+    const float hv[4] = {h.x, h.y, h.z, h.w};
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+    float ov[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float cdf = 0.5f * (1.0f + erff(hv[j] * 0.70710678118654752f));
+      const float pdf = 0.39894228040143268f * __expf(-0.5f * hv[j] * hv[j]);
+      ov[j] = dv[j] * (cdf + hv[j] * pdf);
+    }
+    o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    store4<__nv_bfloat16>(out + 4 * i, o);
   }
 }
 
@@ -363,7 +386,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
 #define LN_CASE(NV)                                                                                                      \
   case NV: {                                                                                                             \
     auto k = layernorm_bwd_kernel<DT, XT, NV>;                                                                           \
-    if (smem > 48 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     k<<<grid, EW_THREADS, smem, s>>>((const DT*)dy, (const XT*)x, gamma, mean, rstd, dx_resid, dx_out,                   \
                                      (__nv_bfloat16*)dx_out_bf16, dgamma, dbeta, rows, cols);                            \
   } break;
@@ -411,6 +434,15 @@ extern "C" int vmae_scale_f32(const float* x, float* y, float alpha, int accumul
   VMAE_CHECK_ARG(n >= 0 && (n == 0 || (x && y)), "vmae_scale_f32: bad args");
   if (n == 0) return VMAE_OK;
   scale_f32_kernel<<<ew_grid(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, alpha, accumulate, n);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+extern "C" int vmae_gelu_bwd(const void* dy, const void* pre, void* out, long long n, void* stream) {
+  VMAE_CHECK_ARG(n >= 0 && n % 4 == 0 && (n == 0 || (dy && pre && out)), "vmae_gelu_bwd: bad args (n must be a multiple of 4)");
+  if (n == 0) return VMAE_OK;
+  gelu_bwd_kernel<<<ew_grid(n / 4, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre,
+                                                                                       (__nv_bfloat16*)out, n);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }

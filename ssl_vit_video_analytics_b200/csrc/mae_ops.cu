@@ -376,11 +376,11 @@ extern "C" int vmae_masked_mse_fwd(const float* clip, const void* pred, int pred
   cudaStream_t s = (cudaStream_t)stream;
   if (pred_dtype == VMAE_DTYPE_BF16) {
     auto k = masked_mse_fwd_kernel<__nv_bfloat16>;
-    if (smem > 48 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, MO_THREADS, smem, s>>>(clip, (const __nv_bfloat16*)pred, mask, acc, (__nv_bfloat16*)diff, B, T, H, W, pt, ps, norm_pix);
   } else if (pred_dtype == VMAE_DTYPE_F32) {
     auto k = masked_mse_fwd_kernel<float>;
-    if (smem > 48 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, MO_THREADS, smem, s>>>(clip, (const float*)pred, mask, acc, (__nv_bfloat16*)diff, B, T, H, W, pt, ps, norm_pix);
   } else {
     return fail(VMAE_ERR_BAD_ARG, "vmae_masked_mse_fwd: bad pred dtype %d", pred_dtype);

@@ -1,0 +1,151 @@
+"""North-star configuration (BASELINE.json): ViT-S/16 VideoMAE with tubelet embedding and encoder-side masking.
+
+The reference has no such module (its MAE encoder is TinyViT and nothing is gathered — SURVEY.md §0 fact 2), so this
+model is assembled from the reference's own blocks and keeps its `forward(x, mask) -> pred` contract:
+  * tubelet embed = Conv3d(3, D, (2,16,16), stride (2,16,16)) evaluated on the VISIBLE tubes only
+    (gather kernel -> tcgen05 GEMM with bias + positional rows in the epilogue);
+  * encoder block = LayerNorm -> Attention -> Mlp exactly as tiny_vit.py:74-130 in token form (x12) + final LayerNorm;
+  * enc_to_dec / factorised positional embeddings / mask-token substitution / decoder / decoder_norm / decoder_pred
+    exactly as mae_vit_adapter.py:24-53,93-115, visible tokens scattered back to their positions;
+  * loss = train_ssl_mae.py:72-84 generalised to (2,16,16) tubelets (`training_loss`).
+Its fp32 oracle is `oracle/restatement.py::videomae_vit_forward` (a restatement, not the reference).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from .mae_vit_adapter import DecoderLayer, DecoderStack, trunc_normal_
+from .tiny_vit import Attention, Mlp
+
+
+class TubeletEmbed(nn.Module):
+    def __init__(self, in_chans, embed_dim, tubelet):
+        super().__init__()
+        self.tubelet = tuple(tubelet)
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=self.tubelet, stride=self.tubelet)
+
+
+class EncoderBlock(nn.Module):
+    """TinyViTBlock in token form (no NCHW round trip): norm1, attn{qkv,proj}, norm2, mlp{fc1,fc2}."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = Attention(dim, key_dim=dim // num_heads, num_heads=num_heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio))
+
+    def forward_tokens(self, t, B, Lq):
+        return ops.transformer_block(t, self.norm1, self.attn.qkv.weight, self.attn.qkv.bias, self.attn.proj, self.norm2,
+                                     self.mlp.fc1, self.mlp.fc2, self.attn.num_heads, B, Lq)
+
+
+DEFAULT_CONFIG = {
+    "dataset": {"clip_len": 16, "image_size": 224},
+    "model": {
+        "embed_dim": 384, "depth": 12, "num_heads": 6, "tubelet": [2, 16, 16],
+        "decoder_embed_dim": 384, "decoder_depth": 4, "decoder_num_heads": 6, "decoder_dropout": 0.0,
+    },
+    "ssl": {"mask_ratio": 0.9, "norm_pix_loss": True},
+}
+
+
+class VideoMAEViT(nn.Module):
+    def __init__(self, config=None):
+        super().__init__()
+        cfg = config or DEFAULT_CONFIG
+        m = cfg["model"]
+        self.clip_len = cfg["dataset"]["clip_len"]
+        self.img_size = cfg["dataset"]["image_size"]
+        self.tubelet = tuple(m.get("tubelet", (2, 16, 16)))
+        pt, ps, ps2 = self.tubelet
+        assert ps == ps2, "square spatial patches only"
+        self.frames_out = self.clip_len // pt
+        self.num_patches = (self.img_size // ps) ** 2
+        self.embed_dim = m.get("embed_dim", 384)
+        self.num_heads = m.get("num_heads", 6)
+        self.depth = m.get("depth", 12)
+        self.decoder_embed_dim = m["decoder_embed_dim"]
+        self.decoder_num_heads = m["decoder_num_heads"]
+        self.decoder_depth = m["decoder_depth"]
+        self.norm_pix_loss = bool(cfg.get("ssl", {}).get("norm_pix_loss", True))
+        E, D = self.embed_dim, self.decoder_embed_dim
+
+        self.patch_embed = TubeletEmbed(3, E, self.tubelet)
+        self.enc_temporal_pos_embed = nn.Parameter(torch.zeros(1, self.frames_out, 1, E))
+        self.enc_spatial_pos_embed = nn.Parameter(torch.zeros(1, 1, self.num_patches, E))
+        self.blocks = nn.ModuleList([EncoderBlock(E, self.num_heads) for _ in range(self.depth)])
+        self.norm = nn.LayerNorm(E)
+
+        self.enc_to_dec = nn.Linear(E, D, bias=True)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, D))
+        self.temporal_pos_embed = nn.Parameter(torch.zeros(1, self.frames_out, 1, D))
+        self.spatial_pos_embed = nn.Parameter(torch.zeros(1, 1, self.num_patches, D))
+        self.decoder_blocks = DecoderStack(
+            lambda: DecoderLayer(D, self.decoder_num_heads, int(D * 4), float(m.get("decoder_dropout", 0.0))), self.decoder_depth)
+        self.decoder_norm = nn.LayerNorm(D)
+        self.decoder_pred = nn.Linear(D, pt * ps * ps * 3, bias=True)
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        for p in (self.enc_temporal_pos_embed, self.enc_spatial_pos_embed, self.temporal_pos_embed, self.spatial_pos_embed,
+                  self.mask_token):
+            trunc_normal_(p, std=0.02)
+        w = self.patch_embed.proj.weight
+        nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+        nn.init.constant_(self.patch_embed.proj.bias, 0)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def visible_indices(self, mask, n_vis=None):
+        """mask [B, T', L] bool (tube mask: identical over T') -> int32 [B, n_vis], ascending visible patch ids.
+        n_vis defaults to the count in clip 0 (one host sync); pass it to stay sync-free (CUDA-graph capture)."""
+        frame = mask[:, 0].to(torch.uint8).contiguous()
+        if n_vis is None:
+            n_vis = int((frame[0] == 0).sum().item())
+        return ops.mask_to_indices(frame, n_vis)
+
+    def forward(self, x, mask, vis_idx=None):
+        """x: fp32 [B, 3, T, H, W]; mask: bool [B, T', L] (True = masked) -> pred [B, T'*L, pt*ps*ps*3]."""
+        B = x.shape[0]
+        Tp, Lp, E, D = self.frames_out, self.num_patches, self.embed_dim, self.decoder_embed_dim
+        pt, ps, _ = self.tubelet
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if vis_idx is None:
+            vis_idx = self.visible_indices(mask)
+        n_vis = vis_idx.shape[1]
+        Lv = Tp * n_vis
+        patches, pos_rows = ops.TubeletGatherFn.apply(x, vis_idx, self.enc_temporal_pos_embed, self.enc_spatial_pos_embed, pt, ps)
+        t = ops.LinearResidualF32Fn.apply(patches, self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos_rows)
+        for blk in self.blocks:
+            t = blk.forward_tokens(t, B, Lv)
+        z = ops.LayerNormFn.apply(t, self.norm.weight, self.norm.bias, self.norm.eps, ops.BF16)
+        z = ops.LinearFn.apply(z, self.enc_to_dec.weight, self.enc_to_dec.bias, L.ACT_NONE)      # bf16 [B*Lv, D]
+        m8 = mask.reshape(B, Tp * Lp).to(torch.uint8).contiguous()
+        x_dec = ops.DecoderInputFn.apply(z, vis_idx, m8, self.temporal_pos_embed, self.spatial_pos_embed, self.mask_token,
+                                         B, Tp, Lp)
+        x_dec = self.decoder_blocks(x_dec)
+        y = ops.LayerNormFn.apply(x_dec, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps, ops.BF16)
+        return ops.linear(y, self.decoder_pred.weight, self.decoder_pred.bias)
+
+    def training_loss(self, x, mask, vis_idx=None):
+        """pred + fused normalised-pixel masked MSE (one scalar); the path bench.py times."""
+        pt, ps, _ = self.tubelet
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = self.forward(x, mask, vis_idx)
+        return ops.masked_mse(pred, x if x.dtype == torch.float32 else x.float(), mask, pt, ps, 1 if self.norm_pix_loss else 0)

@@ -1,0 +1,568 @@
+"""Tensor-level wrappers over the C ABI (include/vmae.h) and the autograd Functions built from them.
+
+Everything here launches hand-written sm_100a kernels from libvmae_sm100a.so on the current CUDA stream. PyTorch is
+used for device memory (caching allocator), streams and autograd bookkeeping only. There is no fallback: a CPU tensor
+or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+# number of kernels of ours launched since reset_launch_count() (bench.py reports it as gpu_launches)
+_launches = 0
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == BF16:
+        return L.DTYPE_BF16
+    if t.dtype == F32:
+        return L.DTYPE_F32
+    raise TypeError(f"unsupported dtype {t.dtype} (bf16 or fp32 only)")
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ssl_vit_video_analytics_b200 ops run on CUDA (sm_100a) tensors only; there is no CPU path")
+
+
+# ======================================================================================================================
+# raw kernels
+# ======================================================================================================================
+def gemm(a, b, M, N, K, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, residual=None, aux_in=None, aux_out=None,
+         out=None, out_dtype=BF16, accumulate=False, act=L.ACT_NONE, k_splits=1):
+    """out[M,N] = epi(A[M,K] @ B[N,K]^T); see vmae_gemm_bf16 in include/vmae.h for operand-major conventions."""
+    _need_cuda(a, b)
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    lib = L.load()
+    rc = lib.vmae_gemm_bf16(_p(a), a.stride(0), a_major, _p(b), b.stride(0), b_major, M, N, K, _p(bias), _p(residual),
+                            residual.stride(0) if residual is not None else 0, _p(aux_in),
+                            aux_in.stride(0) if aux_in is not None else 0, _p(aux_out),
+                            aux_out.stride(0) if aux_out is not None else 0, _p(out), out.stride(0), _dt(out),
+                            1 if accumulate else 0, act, k_splits, _stream())
+    L.check(rc, "vmae_gemm_bf16")
+    _count()
+    return out
+
+
+def _wgrad_splits(tokens: int, n_out: int, k_out: int) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_out + 191) // 192)
+    kb = (tokens + 63) // 64
+    return max(1, min(kb, (2 * 148 + tiles - 1) // tiles))
+
+
+def linear_fwd(x, w_bf16, bias=None, *, act=L.ACT_NONE, residual=None, aux_out=None, out_dtype=BF16):
+    M, K = x.shape
+    N = w_bf16.shape[0]
+    return gemm(x, w_bf16, M, N, K, bias=bias, residual=residual, aux_out=aux_out, act=act,
+                out_dtype=F32 if residual is not None else out_dtype)
+
+
+def linear_dgrad(dy, w_bf16, *, aux_in=None):
+    """dx[M,K] = dy[M,N] @ W[N,K] (optionally * gelu'(aux_in))"""
+    M, N = dy.shape
+    K = w_bf16.shape[1]
+    return gemm(dy, w_bf16, M, K, N, b_major=L.MAJOR_MN, aux_in=aux_in)
+
+
+def linear_wgrad(dy, x, dw=None):
+    """dW[N,K] (+)= dy[M,N]^T @ x[M,K] in fp32 (split-K with red.add)"""
+    M, N = dy.shape
+    K = x.shape[1]
+    if dw is None:
+        dw = torch.zeros((N, K), device=dy.device, dtype=F32)
+    gemm(dy, x, N, K, M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=dw, accumulate=True, k_splits=_wgrad_splits(M, N, K))
+    return dw
+
+
+def colsum(dy, db=None):
+    M, N = dy.shape
+    if db is None:
+        db = torch.zeros((N,), device=dy.device, dtype=F32)
+    L.check(L.load().vmae_colsum_accum(_p(dy), _dt(dy), dy.stride(0), _p(db), M, N, _stream()), "vmae_colsum_accum")
+    _count()
+    return db
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype == BF16:
+        return x if x.is_contiguous() else x.contiguous()
+    x = x.contiguous()
+    assert x.dtype == F32
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    L.check(L.load().vmae_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream()), "vmae_cast_f32_to_bf16")
+    _count()
+    return y
+
+
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype == F32:
+        return x if x.is_contiguous() else x.contiguous()
+    x = x.contiguous()
+    assert x.dtype == BF16
+    y = torch.empty(x.shape, device=x.device, dtype=F32)
+    L.check(L.load().vmae_cast_bf16_to_f32(_p(x), _p(y), x.numel(), _stream()), "vmae_cast_bf16_to_f32")
+    _count()
+    return y
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, out_dtype=BF16, save_stats=True):
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
+    mean = torch.empty((rows,), device=x.device, dtype=F32) if save_stats else None
+    rstd = torch.empty((rows,), device=x.device, dtype=F32) if save_stats else None
+    L.check(L.load().vmae_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows, cols,
+                                        eps, _stream()), "vmae_layernorm_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_resid=None, dgamma=None, dbeta=None, want_bf16=False, want_f32=True):
+    rows, cols = x.shape
+    dx = torch.empty((rows, cols), device=x.device, dtype=F32) if want_f32 else None
+    dx_b = torch.empty((rows, cols), device=x.device, dtype=BF16) if want_bf16 else None
+    if dgamma is None:
+        dgamma = torch.zeros((cols,), device=x.device, dtype=F32)
+    if dbeta is None:
+        dbeta = torch.zeros((cols,), device=x.device, dtype=F32)
+    L.check(L.load().vmae_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx),
+                                        _p(dx_b), _p(dgamma), _p(dbeta), rows, cols, _stream()), "vmae_layernorm_bwd")
+    _count()
+    return dx, dx_b, dgamma, dbeta
+
+
+def attn_fwd(qkv, B, Lq, H, hd):
+    out = torch.empty((B * Lq, H * hd), device=qkv.device, dtype=BF16)
+    lse = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
+    L.check(L.load().vmae_attn_fwd(_p(qkv), _p(out), _p(lse), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream()), "vmae_attn_fwd")
+    _count()
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
+    L.check(L.load().vmae_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, Lq, H, hd,
+                                   1.0 / math.sqrt(hd), _stream()), "vmae_attn_bwd")
+    _count(3)
+    return dqkv
+
+
+# ======================================================================================================================
+# autograd Functions
+# ======================================================================================================================
+def _amp_dtype_out(like_fp32: bool = False):
+    """dtype a Linear-like op should return: bf16 under CUDA autocast (as nn.Linear would), else fp32."""
+    if like_fp32:
+        return F32
+    return BF16 if torch.is_autocast_enabled("cuda") else F32
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b): nn.Linear (+ optional GELU) on the tcgen05 GEMM. x: [..., K] bf16/fp32; y bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        _need_cuda(x, weight)
+        shp = x.shape
+        x2 = cast_bf16(x.reshape(-1, shp[-1]))
+        wb = cast_bf16(weight)
+        bf = bias.float().contiguous() if bias is not None else None
+        pre = torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=BF16) if act == L.ACT_GELU else None
+        y = linear_fwd(x2, wb, bf, act=act, aux_out=pre)
+        ctx.save_for_backward(x2, wb, pre)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = shp
+        ctx.in_dtype = x.dtype
+        return y.reshape(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, pre = ctx.saved_tensors
+        dy2 = cast_bf16(dy.reshape(-1, dy.shape[-1]))
+        if pre is not None:
+            dy2 = gelu_bwd(dy2, pre)
+        dx = linear_dgrad(dy2, wb) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(dy2, x2) if ctx.needs_input_grad[1] else None
+        db = colsum(dy2) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        if dx is not None:
+            dx = dx.reshape(ctx.in_shape)
+            if ctx.in_dtype == F32:
+                dx = cast_f32(dx)
+        return dx, dw, db, None
+
+
+def gelu_bwd(dy_bf16, pre_bf16):
+    """dy * gelu'(pre) (exact erf GELU), bf16 elementwise; used by the unfused LinearFn only."""
+    out = torch.empty_like(dy_bf16)
+    L.check(L.load().vmae_gelu_bwd(_p(dy_bf16), _p(pre_bf16), _p(out), dy_bf16.numel(), _stream()), "vmae_gelu_bwd")
+    _count()
+    return out
+
+
+def linear(x, weight, bias=None, act=L.ACT_NONE):
+    y = LinearFn.apply(x, weight, bias, act)
+    out_dt = _amp_dtype_out()
+    return y if out_dt == BF16 else cast_f32_autograd(y)
+
+
+class _CastF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return cast_f32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return cast_bf16(g)
+
+
+class _CastBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.src = x.dtype
+        return cast_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return cast_f32(g) if ctx.src == F32 else g
+
+
+def cast_f32_autograd(x):
+    return x if x.dtype == F32 else _CastF32.apply(x)
+
+
+def cast_bf16_autograd(x):
+    return x if x.dtype == BF16 else _CastBF16.apply(x)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim; fp32/bf16 in, bf16 or fp32 out."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        _need_cuda(x, weight)
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.dtype not in (BF16, F32):
+            raise TypeError(f"LayerNormFn: dtype {x2.dtype}")
+        x2 = x2.contiguous()
+        g, b = weight.float().contiguous(), bias.float().contiguous()
+        y, mean, rstd = layernorm_fwd(x2, g, b, eps, out_dtype)
+        ctx.save_for_backward(x2, g, mean, rstd)
+        ctx.in_shape = shp
+        ctx.in_dtype = x.dtype
+        return y.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        want_b = ctx.in_dtype == BF16
+        dx, dxb, dg, db = layernorm_bwd(dy2, x2, g, mean, rstd, want_bf16=want_b, want_f32=not want_b)
+        dxo = dxb if want_b else dx
+        return dxo.reshape(ctx.in_shape), dg, db, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
+    if out_dtype is None:
+        out_dtype = F32 if (x.dtype == F32 and not torch.is_autocast_enabled("cuda")) else (x.dtype if x.dtype == BF16 else F32)
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype)
+
+
+class AttentionFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(hd)) v on the packed projection qkv [B, L, 3*H*hd] -> [B, L, H*hd] (bf16)."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads):
+        _need_cuda(qkv)
+        B, Lq, W3 = qkv.shape
+        hd = W3 // (3 * num_heads)
+        q = cast_bf16(qkv)
+        out, lse = attn_fwd(q, B, Lq, num_heads, hd)
+        ctx.save_for_backward(q, out, lse)
+        ctx.dims = (B, Lq, num_heads, hd)
+        ctx.in_dtype = qkv.dtype
+        return out.reshape(B, Lq, num_heads * hd)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, out, lse = ctx.saved_tensors
+        B, Lq, H, hd = ctx.dims
+        d = cast_bf16(dout.reshape(B * Lq, H * hd))
+        dqkv = attn_bwd(q, out, d, lse, B, Lq, H, hd)
+        if ctx.in_dtype == F32:
+            dqkv = cast_f32(dqkv)
+        return dqkv, None
+
+
+def attention(qkv, num_heads):
+    return AttentionFn.apply(qkv, num_heads)
+
+
+class TransformerBlockFn(torch.autograd.Function):
+    """One pre-LN transformer block, forward and backward as a fixed schedule of fused kernels:
+
+        x1 = x  + proj(attn(qkv(LN1(x))))          x2 = x1 + fc2(GELU(fc1(LN2(x1))))
+
+    It is the arithmetic of both TinyViTBlock (tiny_vit.py:108-130) and nn.TransformerEncoderLayer(norm_first=True,
+    activation="gelu") (mae_vit_adapter.py:40-48) with dropout / drop-path inactive. Residual stream fp32 (as the
+    reference's decoder under autocast), GEMM/attention operands bf16, fp32 accumulation.
+    Fusions: bias / bias+GELU(+pre-activation save) / bias+residual in GEMM epilogues, gelu' in the fc2-dgrad epilogue,
+    residual-gradient add + bf16 copy in the LayerNorm backward.
+    """
+
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, B, Lq):
+        _need_cuda(x)
+        D = x.shape[-1]
+        assert x.dtype == F32 and x.is_contiguous() and x.shape[0] == B * Lq
+        hd = D // num_heads
+        f = lambda t: t.float().contiguous()
+        ln1_w, ln1_b, ln2_w, ln2_b = f(ln1_w), f(ln1_b), f(ln2_w), f(ln2_b)
+        qkv_b, proj_b, fc1_b, fc2_b = f(qkv_b), f(proj_b), f(fc1_b), f(fc2_b)
+        wq, wp, w1, w2 = cast_bf16(qkv_w), cast_bf16(proj_w), cast_bf16(fc1_w), cast_bf16(fc2_w)
+        ln1, mean1, rstd1 = layernorm_fwd(x, ln1_w, ln1_b)
+        qkv = linear_fwd(ln1, wq, qkv_b)
+        o, lse = attn_fwd(qkv, B, Lq, num_heads, hd)
+        x1 = linear_fwd(o, wp, proj_b, residual=x)
+        ln2, mean2, rstd2 = layernorm_fwd(x1, ln2_w, ln2_b)
+        h_pre = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
+        act = linear_fwd(ln2, w1, fc1_b, act=L.ACT_GELU, aux_out=h_pre)
+        x2 = linear_fwd(act, w2, fc2_b, residual=x1)
+        ctx.save_for_backward(x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2)
+        ctx.dims = (B, Lq, num_heads, hd)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2) = ctx.saved_tensors
+        B, Lq, H, hd = ctx.dims
+        dx2 = dx2.contiguous()
+        dx2_b = cast_bf16(dx2)
+        # ---- MLP branch
+        dh = linear_dgrad(dx2_b, w2, aux_in=h_pre)          # d(fc1 out) = (dx2 W2) * gelu'(h_pre)
+        dw2 = linear_wgrad(dx2_b, act)
+        db2 = colsum(dx2_b)
+        dln2 = linear_dgrad(dh, w1)
+        dw1 = linear_wgrad(dh, ln2)
+        db1 = colsum(dh)
+        dx1, dx1_b, dg2, dbeta2 = layernorm_bwd(dln2, x1, ln2_w, mean2, rstd2, dx_resid=dx2, want_bf16=True)
+        # ---- attention branch
+        do = linear_dgrad(dx1_b, wp)
+        dwp = linear_wgrad(dx1_b, o)
+        dbp = colsum(dx1_b)
+        dqkv = attn_bwd(qkv, o, do, lse, B, Lq, H, hd)
+        dln1 = linear_dgrad(dqkv, wq)
+        dwq = linear_wgrad(dqkv, ln1)
+        dbq = colsum(dqkv)
+        dx, _, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1)
+        return dx, dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2, None, None, None
+
+
+def transformer_block(x, ln1, qkv_w, qkv_b, proj, ln2, fc1, fc2, num_heads, B, Lq):
+    return TransformerBlockFn.apply(x, ln1.weight, ln1.bias, qkv_w, qkv_b, proj.weight, proj.bias, ln2.weight, ln2.bias,
+                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias, num_heads, B, Lq)
+
+
+class LinearResidualF32Fn(torch.autograd.Function):
+    """fp32 out = x W^T + b + residual (fp32). Used for the tubelet embedding (+pos rows) in the ViT encoder."""
+
+    @staticmethod
+    def forward(ctx, x_bf16, weight, bias, residual):
+        wb = cast_bf16(weight.reshape(weight.shape[0], -1))
+        y = linear_fwd(x_bf16, wb, bias.float().contiguous() if bias is not None else None, residual=residual.contiguous())
+        ctx.save_for_backward(x_bf16, wb)
+        ctx.w_shape = weight.shape
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wb = ctx.saved_tensors
+        dy = dy.contiguous()
+        dyb = cast_bf16(dy)
+        dx = linear_dgrad(dyb, wb) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(dyb, x).reshape(ctx.w_shape) if ctx.needs_input_grad[1] else None
+        db = colsum(dyb) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, dy if ctx.needs_input_grad[3] else None
+
+
+# ---- MAE-specific -----------------------------------------------------------------------------------------------
+def mask_to_indices(mask_frame_u8, n_vis):
+    B, Lp = mask_frame_u8.shape
+    vis = torch.empty((B, n_vis), device=mask_frame_u8.device, dtype=torch.int32)
+    L.check(L.load().vmae_mask_to_indices(_p(mask_frame_u8), _p(vis), B, Lp, n_vis, _stream()), "vmae_mask_to_indices")
+    _count()
+    return vis
+
+
+class TubeletGatherFn(torch.autograd.Function):
+    """visible-tubelet im2col + encoder positional rows. Non-differentiable w.r.t. the clip; the positional tables get
+    their gradient from the rows' gradient (scatter-add)."""
+
+    @staticmethod
+    def forward(ctx, clip, vis_idx, tpos, spos, pt, ps):
+        B, Cc, T, H, W = clip.shape
+        n_vis = vis_idx.shape[1]
+        D = tpos.shape[-1]
+        Tp = T // pt
+        rows = B * Tp * n_vis
+        patches = torch.empty((rows, Cc * pt * ps * ps), device=clip.device, dtype=BF16)
+        pos_rows = torch.empty((rows, D), device=clip.device, dtype=F32)
+        tp2, sp2 = tpos.reshape(Tp, D).float().contiguous(), spos.reshape(-1, D).float().contiguous()
+        L.check(L.load().vmae_gather_tubelets(_p(clip), _p(vis_idx), _p(patches), _p(tp2), _p(sp2), _p(pos_rows), B, T, H, W,
+                                              pt, ps, n_vis, D, _stream()), "vmae_gather_tubelets")
+        _count()
+        ctx.save_for_backward(vis_idx)
+        ctx.dims = (B, Tp, n_vis, D, sp2.shape[0])
+        ctx.shapes = (tpos.shape, spos.shape)
+        ctx.mark_non_differentiable(patches)
+        return patches, pos_rows
+
+    @staticmethod
+    def backward(ctx, _dpatches, dpos_rows):
+        (vis_idx,) = ctx.saved_tensors
+        B, Tp, n_vis, D, Lp = ctx.dims
+        dt = torch.zeros((Tp, D), device=dpos_rows.device, dtype=F32)
+        ds = torch.zeros((Lp, D), device=dpos_rows.device, dtype=F32)
+        L.check(L.load().vmae_pos_rows_bwd(_p(dpos_rows.contiguous()), _p(vis_idx), _p(dt), _p(ds), B, Tp, n_vis, D, _stream()),
+                "vmae_pos_rows_bwd")
+        _count()
+        return None, None, dt.reshape(ctx.shapes[0]), ds.reshape(ctx.shapes[1]), None, None
+
+
+class DecoderInputFn(torch.autograd.Function):
+    """x_dec = visible ? z + (tpos + spos) : mask_token  (mae_vit_adapter.py:97-107). z bf16 rows; fp32 out [B,Tp*L,D]."""
+
+    @staticmethod
+    def forward(ctx, z, vis_idx, mask_u8, tpos, spos, mask_token, B, Tp, Lp):
+        D = z.shape[-1]
+        n_vis = vis_idx.shape[1] if vis_idx is not None else 0
+        x = torch.empty((B, Tp * Lp, D), device=z.device, dtype=F32)
+        z = cast_bf16(z)
+        tp2, sp2, mt = tpos.reshape(Tp, D).float().contiguous(), spos.reshape(Lp, D).float().contiguous(), mask_token.reshape(D).float().contiguous()
+        L.check(L.load().vmae_decoder_input_fwd(_p(z), _p(vis_idx), _p(mask_u8), _p(tp2), _p(sp2), _p(mt), _p(x), B, Tp, Lp, n_vis,
+                                                D, _stream()), "vmae_decoder_input_fwd")
+        _count()
+        ctx.save_for_backward(vis_idx, mask_u8)
+        ctx.dims = (B, Tp, Lp, n_vis, D, z.shape)
+        ctx.shapes = (tpos.shape, spos.shape, mask_token.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        vis_idx, mask_u8 = ctx.saved_tensors
+        B, Tp, Lp, n_vis, D, zshape = ctx.dims
+        dx = dx.contiguous()
+        dz = torch.empty(zshape, device=dx.device, dtype=BF16)
+        dt = torch.zeros((Tp, D), device=dx.device, dtype=F32)
+        ds = torch.zeros((Lp, D), device=dx.device, dtype=F32)
+        dm = torch.zeros((D,), device=dx.device, dtype=F32)
+        L.check(L.load().vmae_decoder_input_bwd(_p(dx), _p(vis_idx), _p(mask_u8), _p(dz), _p(dt), _p(ds), _p(dm), B, Tp, Lp, n_vis,
+                                                D, _stream()), "vmae_decoder_input_bwd")
+        _count()
+        return dz, None, None, dt.reshape(ctx.shapes[0]), ds.reshape(ctx.shapes[1]), dm.reshape(ctx.shapes[2]), None, None, None
+
+
+class MaskedMSEFn(torch.autograd.Function):
+    """Fused patchify + per-patch normalise + masked MSE (train_ssl_mae.py:26-31,72-84). Returns the scalar loss."""
+
+    @staticmethod
+    def forward(ctx, pred, clip, mask_u8, pt, ps, norm_pix):
+        _need_cuda(pred, clip, mask_u8)
+        B, Cc, T, H, W = clip.shape
+        pred_c = pred.contiguous()
+        clip = clip.contiguous()
+        assert clip.dtype == F32 and Cc == 3
+        D = pt * ps * ps * 3
+        acc = torch.zeros((2,), device=pred.device, dtype=F32)
+        diff = torch.empty(pred_c.shape, device=pred.device, dtype=BF16)
+        lib = L.load()
+        L.check(lib.vmae_masked_mse_fwd(_p(clip), _p(pred_c), _dt(pred_c), _p(mask_u8), _p(acc), _p(diff), B, T, H, W, pt, ps, norm_pix,
+                                        _stream()), "vmae_masked_mse_fwd")
+        loss = torch.empty((1,), device=pred.device, dtype=F32)
+        scale = torch.empty((1,), device=pred.device, dtype=F32)
+        L.check(lib.vmae_masked_mse_finalize(_p(acc), _p(loss), _p(scale), D, _stream()), "vmae_masked_mse_finalize")
+        _count(2)
+        ctx.save_for_backward(diff, scale)
+        ctx.pred_dtype = pred.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        diff, scale = ctx.saved_tensors
+        g = gout.reshape(1).float().contiguous()
+        dpred = torch.empty_like(diff)
+        L.check(L.load().vmae_masked_mse_bwd(_p(diff), _p(scale), _p(g), _p(dpred), diff.numel(), _stream()), "vmae_masked_mse_bwd")
+        _count()
+        if ctx.pred_dtype == F32:
+            dpred = cast_f32(dpred)
+        return dpred, None, None, None, None, None
+
+
+def masked_mse(pred, clip, mask, pt, ps, norm_pix=1):
+    m = mask.reshape(mask.shape[0], -1)
+    m8 = m.to(torch.uint8) if m.dtype != torch.uint8 else m
+    return MaskedMSEFn.apply(pred, clip, m8.contiguous(), pt, ps, norm_pix)
+
+
+class GaussianNoiseFn(torch.autograd.Function):
+    """z' = z + sigma * eps, eps ~ N(0, I) from Philox (privacy/feature_noise.py:4-7); gradient is the identity."""
+
+    @staticmethod
+    def forward(ctx, z, sigma, seed, offset):
+        _need_cuda(z)
+        zc = z.contiguous()
+        out = torch.empty_like(zc)
+        L.check(L.load().vmae_add_gaussian_noise(_p(zc), _p(out), _dt(zc), None, zc.numel(), float(sigma), int(seed), int(offset),
+                                                 _stream()), "vmae_add_gaussian_noise")
+        _count()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None, None
+
+
+def scale_f32(x, alpha, out=None, accumulate=False):
+    _need_cuda(x)
+    xc = x.contiguous()
+    if out is None:
+        out = torch.empty_like(xc)
+    L.check(L.load().vmae_scale_f32(_p(xc), _p(out), float(alpha), 1 if accumulate else 0, xc.numel(), _stream()), "vmae_scale_f32")
+    _count()
+    return out
