@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA modules against the CPU oracle restatement (and the live-reference goldens) on the same seeded
+weights, clips and masks. Gates (BASELINE.json north_star): mask/gather indices bit-exact; relative loss error <= 1e-2;
+gradient cosine >= 0.999 globally and per module group (per tensor only above a norm floor)."""
+import os
+
+import pytest
+import torch
+
+from helpers import CFG1, TINY_CFG, build_ours, cosine, grad_report
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-2
+COS_MIN = 0.999
+
+
+def _run_ours_tinyvideomae(model, clip, mask, autocast=True):
+    model = model.cuda().train()
+    from ssl_vit_video_analytics_b200 import ops
+
+    clip_d, mask_d = clip.cuda(), mask.cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        pred = model(clip_d, mask_d)
+    loss = ops.masked_mse(pred, clip_d, mask_d, 1, 8, 1)
+    loss.backward()
+    grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    return pred.detach().float().cpu(), float(loss), grads
+
+
+def _oracle_tinyvideomae(sd, clip, mask, cfg):
+    sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and "running" not in k else v) for k, v in sd.items()}
+    m = cfg["model"]
+    pred = R.tiny_video_mae_forward(sdg, clip, mask, m["decoder_depth"], m["decoder_num_heads"])
+    loss = R.masked_mse(pred, clip, mask, 1, 8, True)
+    loss.backward()
+    grads = {k: v.grad for k, v in sdg.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    return pred.detach(), float(loss), grads
+
+
+def test_tinyvideomae_tiny_vs_live_reference_golden(golden_dir):
+    tiny = torch.load(os.path.join(golden_dir, "stack1_tiny.pt"), weights_only=False)
+    model = build_ours(TINY_CFG, seed=tiny["seed"])
+    model.load_state_dict(R.perturb_state_dict(model.state_dict(), seed=tiny["perturb_seed"]))
+    pred, loss, grads = _run_ours_tinyvideomae(model, tiny["clip"], tiny["mask"])
+    assert cosine(pred, tiny["pred"]) >= COS_MIN
+    assert abs(loss - float(tiny["loss"])) <= LOSS_RTOL * abs(float(tiny["loss"]))
+    floor = 1e-3 * max(tiny["grad_norms"].values())
+    for k, gref in tiny["grads"].items():
+        if float(gref.norm()) >= floor:
+            assert cosine(grads[k], gref) >= 0.99, (k, cosine(grads[k], gref))
+    for k, n in tiny["grad_norms"].items():
+        if n >= floor and k in grads:
+            assert float(grads[k].norm()) == pytest.approx(n, rel=0.1), k
+
+
+@pytest.mark.parametrize("autocast", [True, False])
+def test_tinyvideomae_cfg1_vs_oracle(autocast):
+    """BASELINE config 1 (B=2, T=8, 112x112, mask 0.9) on the drop-in model, perturbed init."""
+    model = build_ours(CFG1, seed=0)
+    sd = R.perturb_state_dict(model.state_dict(), seed=1234)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(0)
+    clip = torch.randn(2, 3, 8, 112, 112, generator=g)
+    torch.manual_seed(42)
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+
+    mask = get_tube_mask(2, 8, 196, 0.9)
+    pred_o, loss_o, grads_o = _oracle_tinyvideomae(sd, clip, mask, CFG1)
+    pred, loss, grads = _run_ours_tinyvideomae(model, clip, mask, autocast)
+    assert pred.shape == (2, 8 * 196, 192)
+    assert cosine(pred, pred_o) >= COS_MIN
+    assert abs(loss - loss_o) <= LOSS_RTOL * abs(loss_o), (loss, loss_o)
+    glob, per = grad_report(grads, grads_o)
+    assert glob >= COS_MIN, (glob, per)
+    for grp, c in per.items():
+        assert c >= COS_MIN - (0.004 if grp in ("stem", "stage0", "stage1") else 0.0), (grp, c, per)
+    # unused stage 3 gets no gradient, exactly like the reference
+    assert all(not k.startswith("encoder.stages.3.") for k in grads)
+
+
+def _small_b_cfg():
+    return {"dataset": {"clip_len": 4, "image_size": 64},
+            "model": {"embed_dim": 384, "depth": 2, "num_heads": 6, "tubelet": [2, 16, 16], "decoder_embed_dim": 384, "decoder_depth": 2,
+                      "decoder_num_heads": 6, "decoder_dropout": 0.0},
+            "ssl": {"mask_ratio": 0.75, "norm_pix_loss": True}}
+
+
+def _run_model_b(cfg, B, seed_clip=0, seed_mask=42, ratio=0.75):
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg)
+    sd = R.perturb_state_dict(model.state_dict(), seed=99)
+    model.load_state_dict(sd)
+    T, S = cfg["dataset"]["clip_len"], cfg["dataset"]["image_size"]
+    pt, ps, _ = cfg["model"]["tubelet"]
+    g = torch.Generator().manual_seed(seed_clip)
+    clip = torch.randn(B, 3, T, S, S, generator=g)
+    torch.manual_seed(seed_mask)
+    mask = get_tube_mask(B, T // pt, (S // ps) ** 2, ratio)
+    return model, sd, clip, mask, visible_indices(mask)
+
+
+def test_videomae_vit_small_vs_restatement():
+    cfg = _small_b_cfg()
+    model, sd, clip, mask, vis_host = _run_model_b(cfg, B=3)
+    m = cfg["model"]
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pred_o = R.videomae_vit_forward(sdg, clip, mask, m["depth"], m["num_heads"], m["decoder_depth"], m["decoder_num_heads"], tuple(m["tubelet"]))
+    loss_o = R.masked_mse(pred_o, clip, mask, 2, 16, True)
+    loss_o.backward()
+    grads_o = {k: v.grad for k, v in sdg.items() if v.grad is not None}
+
+    model = model.cuda().train()
+    clip_d, mask_d = clip.cuda(), mask.cuda()
+    vis_dev = model.visible_indices(mask_d)
+    assert torch.equal(vis_dev.cpu(), vis_host)                       # gather indices bit-exact
+    loss = model.training_loss(clip_d, mask_d, vis_dev)
+    loss.backward()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = model(clip_d, mask_d)
+    assert cosine(pred.float().cpu(), pred_o.detach()) >= COS_MIN
+    assert abs(float(loss) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o)), (float(loss), float(loss_o))
+    grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads) == set(grads_o)
+    glob, per = grad_report(grads, grads_o)
+    assert glob >= COS_MIN, (glob, per)
+    for grp, c in per.items():
+        assert c >= COS_MIN, (grp, c)
+
+
+def test_videomae_vit_full_size_properties():
+    """BASELINE config 2 shapes (16x224x224, tubelet 2x16x16, mask 0.9) at B=4: size-independent properties."""
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+    from ssl_vit_video_analytics_b200.models.videomae_vit import DEFAULT_CONFIG
+
+    model, sd, clip, mask, vis = _run_model_b(DEFAULT_CONFIG, B=4, ratio=0.9)
+    assert vis.shape == (4, 20)
+    model = model.cuda().train()
+    clip_d, mask_d = clip.cuda(), mask.cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = model(clip_d, mask_d)
+    assert pred.shape == (4, 1568, 1536) and pred.dtype == torch.bfloat16 and torch.isfinite(pred.float()).all()
+    # (1) clips are independent: permuting the batch permutes the predictions
+    perm = torch.tensor([2, 0, 3, 1], device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred_p = model(clip_d[perm].contiguous(), mask_d[perm].contiguous())
+    assert torch.equal(pred_p, pred[perm])
+    # (2) masked pixels are invisible to the model: changing them changes no prediction
+    from oracle.restatement import patchify
+
+    clip2 = clip.clone()
+    B, C, T, H, W = clip.shape
+    tok_mask = mask.reshape(B, 8, 14, 14)
+    pix_mask = tok_mask.repeat_interleave(2, 1).repeat_interleave(16, 2).repeat_interleave(16, 3)[:, None].expand_as(clip)
+    clip2[pix_mask] = 7.0
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred2 = model(clip2.cuda(), mask_d)
+    assert torch.equal(pred2, pred)
+    # (3) the loss equals the oracle's loss formula applied to our prediction
+    loss = model.training_loss(clip_d, mask_d)
+    ref = R.masked_mse(pred.float().cpu(), clip, mask, 2, 16, True)
+    assert float(loss) == pytest.approx(float(ref), rel=1e-4)
+    loss.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
