@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — VideoMAE ViT-S pretraining step throughput (clips/s), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W                 our sm_100a path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W  the CPU oracle port of the same step on the host cores
+
+A "step" is one full training step of the north-star configuration (BASELINE config 2): ViT-S/16 VideoMAE,
+16x224x224 clips, tubelet 2x16x16, tube mask 0.9, per-GPU batch 64, bf16 GEMM/attention operands with fp32 accumulation:
+forward, fused masked-MSE loss, backward, (N>1: bucketed gradient allreduce overlapped with backward), AdamW update.
+Synthetic clips and random-init weights (there is no dataset/checkpoint access). One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "videomae_vit_s_pretrain_clips_per_sec"
+UNIT = "clips/s"
+PER_GPU_BATCH = 64
+WORKLOAD = "ViT-S/16 VideoMAE pretrain step, 16x224x224, tubelet 2x16x16, mask 0.9 (BASELINE configs[1]; configs[2] for N>1)"
+STEP_GFLOP_PER_CLIP = 139.96  # 3 x 46.65 GFLOP forward
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.file = index, None, None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(self.index)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        rows = [r.strip().split(", ") for r in self.file.read().strip().splitlines() if r.strip()]
+        self.file.close()
+        os.unlink(self.file.name)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(batch, cfg, seed):
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
+
+    T, S = cfg["dataset"]["clip_len"], cfg["dataset"]["image_size"]
+    pt, ps, _ = cfg["model"]["tubelet"]
+    g = torch.Generator().manual_seed(seed)
+    clip = torch.randn(batch, 3, T, S, S, generator=g)
+    torch.manual_seed(42 + seed)  # rank-seeded masks
+    mask = get_tube_mask(batch, T // pt, (S // ps) ** 2, cfg["ssl"]["mask_ratio"])
+    return clip, mask, visible_indices(mask)
+
+
+# ======================================================================================================================
+# reference arm: the CPU oracle port of the same step on the host cores
+# ======================================================================================================================
+def cpu_reference_step_factory(cfg, batch, threads):
+    from oracle import restatement as R
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg)  # parameter container only (constructed on CPU; its forward is never called here)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-4, weight_decay=0.05)
+    clip, mask, _ = make_inputs(batch, cfg, seed=0)
+    m = cfg["model"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pred = R.videomae_vit_forward(sd, clip, mask, m["depth"], m["num_heads"], m["decoder_depth"], m["decoder_num_heads"], tuple(m["tubelet"]))
+        loss = R.masked_mse(pred, clip, mask, m["tubelet"][0], m["tubelet"][1], True)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def time_cpu_reference(cfg, batch, steps, warmup, threads):
+    step = cpu_reference_step_factory(cfg, batch, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 2
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    val, ms = time_cpu_reference(cfg, batch, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_step_batch": batch, "device": "cpu"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"oracle/restatement.py videomae_vit_forward + masked MSE + backward + AdamW, fp32, batch {batch} clips/step, "
+                                   f"{steps} steps after {warmup} warm-up (capped from the requested {args.steps}/{args.warmup})"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================================
+# our arm
+# ======================================================================================================================
+def run_ours(args, cfg):
+    import torch.distributed as dist
+
+    from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+    from ssl_vit_video_analytics_b200.parallel import GradientBucketer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a B200: the sm_100a kernels have no fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = PER_GPU_BATCH if args.batch is None else args.batch
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg).to(dev).train()
+    ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+    clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
+    clip_pinned = [clip_h.pin_memory(), clip_h.clone().pin_memory()]
+    mask_d, vis_d = mask_h.to(dev), vis_h.to(dev)
+    clip_d = clip_h.to(dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(clip):
+        ddp.zero_grad()
+        loss = model.training_loss(clip, mask_d, vis_d)
+        loss.backward()
+        ddp.finish_gradient_sync()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        loss = step(clip_d)
+    barrier()
+
+    # ---- value: inputs resident in HBM (the 616 MB clip + ~20 GB of activations exceed the 126 MB L2 every step)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(clip_d)
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss)
+
+    # ---- e2e: pinned-host clip -> device every step, loss read back every step; the copy of step i+1 is issued on a
+    #      side stream while step i computes (the loader-prefetch pattern of train_ssl_mae.py:67 non_blocking copies)
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(clip_d), torch.empty_like(clip_d)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            bufs[i % 2].copy_(clip_pinned[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream(dev)
+        for b in range(2):
+            consumed[b].record(cur)
+        issue_copy(0)
+        last = 0.0
+        for i in range(n):
+            if i + 1 < n:
+                issue_copy(i + 1)
+            cur.wait_event(ready[i % 2])
+            loss = step(bufs[i % 2])
+            consumed[i % 2].record(cur)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            cur.synchronize()  # the caller reads the loss every step (train_ssl_mae.py:91 loss.item())
+            last = float(loss_host)
+        return last
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    _ = time.perf_counter() - t0
+
+    # ---- roofline leg: the same step with CUDA events around every launch of ours (separate region: events perturb)
+    ops.profile_start()
+    for _ in range(2):
+        step(clip_d)
+    prof = ops.profile_stop()
+    for v in prof.values():
+        v["ms"] /= 2.0
+        v["launches"] /= 2.0
+        v["work"] /= 2.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    tensor_classes = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "attn_fwd", "attn_bwd"]
+    dom = max((k for k in tensor_classes if k in prof), key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = d["work"] / (d["ms"] / 1e3) / 1e12
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "launches_per_step": d["launches"], "ms_per_step": d["ms"],
+                "step_frac_of_tensor_roofline": (B * STEP_GFLOP_PER_CLIP / 1e3) / (ms_step / 1e3) / peaks["bf16_tflops_sustained"],
+                "by_kernel_class": {k: {"ms_per_step": round(v["ms"], 3), "launches_per_step": v["launches"],
+                                        ("tflops" if k in tensor_classes else "gbs"): round(v["work"] / (v["ms"] / 1e3) / (1e12 if k in tensor_classes else 1e9), 1)}
+                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "l2_policy": "inputs larger than L2 (616 MB clip batch, >10 GB activations per step)", "optimizer": "AdamW(fused)",
+                   "final_loss": final_loss},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps, "note": "pinned fp32 clip batch copied H2D every step (double-buffered on a copy stream), loss read back every step"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        try:
+            v, ms = time_cpu_reference(cfg, 2, 3, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "oracle/restatement.py (fp32 PyTorch CPU port of the same step incl. AdamW), batch 2 clips/step, 3 steps after 1 warm-up"}
+        except Exception as ex:  # the baseline must never take the measured line down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {ex!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    from ssl_vit_video_analytics_b200.models.videomae_vit import DEFAULT_CONFIG
+
+    if args.impl == "reference":
+        run_reference(args, DEFAULT_CONFIG)
+    else:
+        run_ours(args, DEFAULT_CONFIG)
+
+
+if __name__ == "__main__":
+    main()

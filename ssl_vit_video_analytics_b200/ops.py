@@ -34,6 +34,37 @@ def _count(n: int = 1) -> None:
     _launches += n
 
 
+# optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline leg)
+_PROF = None
+
+
+def profile_start() -> None:
+    global _PROF
+    _PROF = {}
+
+
+def profile_stop() -> dict:
+    """-> {kernel class: {"ms": total device ms, "launches": n, "work": total flops (or bytes)}}"""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (rec or {}).items():
+        out[name] = {"ms": sum(e0.elapsed_time(e1) for e0, e1, _ in evs), "launches": len(evs), "work": float(sum(w for _, _, w in evs))}
+    return out
+
+
+def _run(name: str, work: float, call):
+    if _PROF is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = call()
+    e1.record()
+    _PROF.setdefault(name, []).append((e0, e1, work))
+    return rc
+
+
 def _p(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -67,11 +98,12 @@ def gemm(a, b, M, N, K, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, resi
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     lib = L.load()
-    rc = lib.vmae_gemm_bf16(_p(a), a.stride(0), a_major, _p(b), b.stride(0), b_major, M, N, K, _p(bias), _p(residual),
-                            residual.stride(0) if residual is not None else 0, _p(aux_in),
-                            aux_in.stride(0) if aux_in is not None else 0, _p(aux_out),
-                            aux_out.stride(0) if aux_out is not None else 0, _p(out), out.stride(0), _dt(out),
-                            1 if accumulate else 0, act, k_splits, _stream())
+    kind = "gemm_wgrad" if a_major == L.MAJOR_MN else ("gemm_dgrad" if b_major == L.MAJOR_MN else "gemm_fwd")
+    rc = _run(kind, 2.0 * M * N * K, lambda: lib.vmae_gemm_bf16(
+        _p(a), a.stride(0), a_major, _p(b), b.stride(0), b_major, M, N, K, _p(bias), _p(residual),
+        residual.stride(0) if residual is not None else 0, _p(aux_in), aux_in.stride(0) if aux_in is not None else 0, _p(aux_out),
+        aux_out.stride(0) if aux_out is not None else 0, _p(out), out.stride(0), _dt(out), 1 if accumulate else 0, act, k_splits,
+        _stream()))
     L.check(rc, "vmae_gemm_bf16")
     _count()
     return out
@@ -111,7 +143,8 @@ def colsum(dy, db=None):
     M, N = dy.shape
     if db is None:
         db = torch.zeros((N,), device=dy.device, dtype=F32)
-    L.check(L.load().vmae_colsum_accum(_p(dy), _dt(dy), dy.stride(0), _p(db), M, N, _stream()), "vmae_colsum_accum")
+    L.check(_run("colsum", float(M) * N * dy.element_size(), lambda: L.load().vmae_colsum_accum(
+        _p(dy), _dt(dy), dy.stride(0), _p(db), M, N, _stream())), "vmae_colsum_accum")
     _count()
     return db
 
@@ -123,7 +156,7 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     assert x.dtype == F32
     y = torch.empty(x.shape, device=x.device, dtype=BF16)
-    L.check(L.load().vmae_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream()), "vmae_cast_f32_to_bf16")
+    L.check(_run("cast", 6.0 * x.numel(), lambda: L.load().vmae_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream())), "vmae_cast_f32_to_bf16")
     _count()
     return y
 
@@ -145,8 +178,8 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, out_dtype=BF16, save_stats=True):
     y = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
     mean = torch.empty((rows,), device=x.device, dtype=F32) if save_stats else None
     rstd = torch.empty((rows,), device=x.device, dtype=F32) if save_stats else None
-    L.check(L.load().vmae_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows, cols,
-                                        eps, _stream()), "vmae_layernorm_fwd")
+    L.check(_run("layernorm_fwd", float(rows) * cols * (x.element_size() + y.element_size()), lambda: L.load().vmae_layernorm_fwd(
+        _p(x), _dt(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows, cols, eps, _stream())), "vmae_layernorm_fwd")
     _count()
     return y, mean, rstd
 
@@ -159,8 +192,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_resid=None, dgamma=None, dbeta
         dgamma = torch.zeros((cols,), device=x.device, dtype=F32)
     if dbeta is None:
         dbeta = torch.zeros((cols,), device=x.device, dtype=F32)
-    L.check(L.load().vmae_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx),
-                                        _p(dx_b), _p(dgamma), _p(dbeta), rows, cols, _stream()), "vmae_layernorm_bwd")
+    nbytes = float(rows) * cols * (dy.element_size() + x.element_size() + (4 if dx_resid is not None else 0) + (4 if want_f32 else 0)
+                                   + (2 if want_bf16 else 0))
+    L.check(_run("layernorm_bwd", nbytes, lambda: L.load().vmae_layernorm_bwd(
+        _p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx), _p(dx_b), _p(dgamma), _p(dbeta), rows, cols,
+        _stream())), "vmae_layernorm_bwd")
     _count()
     return dx, dx_b, dgamma, dbeta
 
@@ -168,7 +204,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_resid=None, dgamma=None, dbeta
 def attn_fwd(qkv, B, Lq, H, hd):
     out = torch.empty((B * Lq, H * hd), device=qkv.device, dtype=BF16)
     lse = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
-    L.check(L.load().vmae_attn_fwd(_p(qkv), _p(out), _p(lse), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream()), "vmae_attn_fwd")
+    L.check(_run("attn_fwd", 4.0 * B * H * Lq * Lq * hd, lambda: L.load().vmae_attn_fwd(
+        _p(qkv), _p(out), _p(lse), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream())), "vmae_attn_fwd")
     _count()
     return out, lse
 
@@ -176,8 +213,8 @@ def attn_fwd(qkv, B, Lq, H, hd):
 def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
-    L.check(L.load().vmae_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, Lq, H, hd,
-                                   1.0 / math.sqrt(hd), _stream()), "vmae_attn_bwd")
+    L.check(_run("attn_bwd", 10.0 * B * H * Lq * Lq * hd, lambda: L.load().vmae_attn_bwd(
+        _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream())), "vmae_attn_bwd")
     _count(3)
     return dqkv
 
@@ -512,8 +549,8 @@ class MaskedMSEFn(torch.autograd.Function):
         acc = torch.zeros((2,), device=pred.device, dtype=F32)
         diff = torch.empty(pred_c.shape, device=pred.device, dtype=BF16)
         lib = L.load()
-        L.check(lib.vmae_masked_mse_fwd(_p(clip), _p(pred_c), _dt(pred_c), _p(mask_u8), _p(acc), _p(diff), B, T, H, W, pt, ps, norm_pix,
-                                        _stream()), "vmae_masked_mse_fwd")
+        L.check(_run("masked_mse_fwd", float(clip.numel()) * 4 + float(pred_c.numel()) * (pred_c.element_size() + 2), lambda: lib.vmae_masked_mse_fwd(
+            _p(clip), _p(pred_c), _dt(pred_c), _p(mask_u8), _p(acc), _p(diff), B, T, H, W, pt, ps, norm_pix, _stream())), "vmae_masked_mse_fwd")
         loss = torch.empty((1,), device=pred.device, dtype=F32)
         scale = torch.empty((1,), device=pred.device, dtype=F32)
         L.check(lib.vmae_masked_mse_finalize(_p(acc), _p(loss), _p(scale), D, _stream()), "vmae_masked_mse_finalize")
