@@ -1,0 +1,258 @@
+"""GPU: every kernel behind the C ABI against a plain PyTorch fp32 reference of the same op (bf16 tolerance for the
+tensor-core kernels, fp32 tolerance for the reductions), including ragged / tail shapes."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1.5e-2   # relative to the largest reference magnitude
+F32_TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def env():
+    from ssl_vit_video_analytics_b200 import _lib, ops
+
+    dev = torch.device("cuda:0")
+    return ops, _lib, dev, torch.Generator(device="cuda").manual_seed(0)
+
+
+def relerr(got, ref):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all()
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 384, 384), (1000, 1152, 384), (512, 1536, 384), (384, 384, 1536), (300, 192, 384),
+                                   (128, 96, 200), (77, 576, 72)])
+def test_gemm_forward_epilogues(env, M, N, K):
+    ops, L, dev, g = env
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev, generator=g)
+    res = torch.randn(M, N, device=dev, generator=g)
+    ref = x.float() @ w.float().t()
+    assert relerr(ops.gemm(x, w, M, N, K), ref) < BF16_TOL
+    assert relerr(ops.gemm(x, w, M, N, K, bias=b), ref + b) < BF16_TOL
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    y = ops.gemm(x, w, M, N, K, bias=b, act=L.ACT_GELU, aux_out=pre)
+    assert relerr(y, F.gelu(ref + b)) < BF16_TOL and relerr(pre, ref + b) < BF16_TOL
+    y32 = ops.gemm(x, w, M, N, K, bias=b, residual=res, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32 and relerr(y32, ref + b + res) < 1e-4
+    h = torch.randn(M, N, device=dev, generator=g).bfloat16()
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).sum().backward()
+    assert relerr(ops.gemm(x, w, M, N, K, aux_in=h), ref * hf.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,Np,Kp", [(128, 64, 64), (1000, 1152, 384), (512, 1536, 384), (384, 384, 1536), (300, 192, 384)])
+def test_gemm_dgrad_mn_major_b(env, M, Np, Kp):
+    ops, L, dev, g = env
+    dy = torch.randn(M, Np, device=dev, generator=g).bfloat16()
+    w = (torch.randn(Np, Kp, device=dev, generator=g) * 0.05).bfloat16()
+    assert relerr(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < BF16_TOL
+
+
+@pytest.mark.parametrize("T,Np,Kp", [(64, 128, 64), (4096, 1152, 384), (10240, 1536, 384), (3000, 384, 1536), (1000, 192, 384), (50, 64, 72)])
+def test_gemm_wgrad_split_k_accumulates(env, T, Np, Kp):
+    ops, L, dev, g = env
+    dy = (torch.randn(T, Np, device=dev, generator=g) * 0.1).bfloat16()
+    x = torch.randn(T, Kp, device=dev, generator=g).bfloat16()
+    dw = torch.ones(Np, Kp, device=dev)
+    ops.linear_wgrad(dy, x, dw)                       # accumulates into an existing gradient buffer
+    assert relerr(dw, dy.float().t() @ x.float() + 1.0) < 1e-4
+
+
+def test_gemm_rejects_bad_arguments(env):
+    ops, L, dev, g = env
+    x = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.gemm(x, x, 128, 60, 64)
+    with pytest.raises(RuntimeError, match="accumulate"):
+        ops.gemm(x, x, 128, 128, 64, k_splits=2)
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 384), (333, 192), (64, 576), (50, 512), (7, 1024), (1, 96)])
+def test_layernorm_fwd_bwd(env, rows, cols):
+    ops, L, dev, g = env
+    x = torch.randn(rows, cols, device=dev, generator=g) * 2 + 0.5
+    gm, bt = torch.randn(cols, device=dev, generator=g), torch.randn(cols, device=dev, generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x, gm, bt)
+    xr, gr, br = x.clone().requires_grad_(True), gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (cols,), gr, br, 1e-5)
+    assert relerr(y, yr) < BF16_TOL
+    y32, _, _ = ops.layernorm_fwd(x, gm, bt, out_dtype=torch.float32)
+    assert relerr(y32, yr) < F32_TOL
+    dy = torch.randn(rows, cols, device=dev, generator=g).bfloat16()
+    res = torch.randn(rows, cols, device=dev, generator=g)
+    yr.backward(dy.float())
+    dx, dxb, dg, db = ops.layernorm_bwd(dy, x, gm, mean, rstd, dx_resid=res, want_bf16=True)
+    assert relerr(dx, xr.grad + res) < F32_TOL and relerr(dxb, xr.grad + res) < BF16_TOL
+    assert relerr(dg, gr.grad) < 1e-4 and relerr(db, br.grad) < 1e-4
+
+
+def _ref_attn(qkv, H):
+    B, Lq, W3 = qkv.shape
+    hd = W3 // (3 * H)
+    q, k, v = qkv.reshape(B, Lq, 3, H, hd).permute(2, 0, 3, 1, 4).float()
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, Lq, H * hd), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,Lq,H,hd", [(1, 16, 1, 64), (1, 64, 1, 64), (1, 100, 2, 64), (2, 160, 6, 64), (2, 300, 3, 64), (2, 1568, 6, 64),
+                                       (1, 128, 1, 32), (3, 196, 12, 32), (2, 784, 6, 32), (1, 49, 18, 32)])
+def test_flash_attention_fwd_bwd(env, B, Lq, H, hd):
+    ops, L, dev, g = env
+    qkv = torch.randn(B, Lq, 3 * H * hd, device=dev, generator=g).bfloat16()
+    dout = torch.randn(B * Lq, H * hd, device=dev, generator=g).bfloat16()
+    out, lse = ops.attn_fwd(qkv, B, Lq, H, hd)
+    qf = qkv.float().requires_grad_(True)
+    ro, rl = _ref_attn(qf, H)
+    assert relerr(out.view(B, Lq, -1), ro) < BF16_TOL
+    assert float((lse - rl).abs().max()) < 1e-2
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)
+    ro.backward(dout.float().view(B, Lq, -1))
+    for i, name in enumerate("qkv"):
+        sl = slice(i * H * hd, (i + 1) * H * hd)
+        assert relerr(dqkv[..., sl], qf.grad[..., sl]) < 2.5e-2, name
+
+
+def test_attention_rejects_unsupported_head_dim(env):
+    ops, L, dev, g = env
+    qkv = torch.zeros(1, 16, 3 * 48, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.attn_fwd(qkv, 1, 16, 1, 48)
+
+
+@pytest.mark.parametrize("B,T,S,pt,ps,norm", [(2, 8, 112, 1, 8, 1), (2, 4, 64, 2, 16, 1), (1, 2, 32, 1, 8, 2), (1, 2, 32, 1, 8, 0)])
+def test_masked_mse_matches_reference_formula(env, B, T, S, pt, ps, norm):
+    from oracle import restatement as R
+
+    ops, L, dev, g = env
+    clip = torch.randn(B, 3, T, S, S, device=dev, generator=g)
+    N, D = (T // pt) * (S // ps) ** 2, pt * ps * ps * 3
+    pred = torch.randn(B, N, D, device=dev, generator=g).bfloat16().requires_grad_(True)
+    mask = torch.rand(B, N, device=dev, generator=g) < 0.9
+    loss = ops.masked_mse(pred, clip, mask, pt, ps, norm)
+    (loss * 3.0).backward()
+    pr = pred.detach().float().cpu().requires_grad_(True)
+    tgt = R.patchify(clip.cpu(), pt, ps)
+    if norm:
+        tgt = R.normalise_target(tgt, unbiased=(norm == 1))
+    lm = ((pr - tgt) ** 2).mean(-1)
+    lref = (lm * mask.cpu()).sum() / (mask.cpu().sum() + 1e-6)
+    (lref * 3.0).backward()
+    assert float(loss) == pytest.approx(float(lref), rel=1e-4)
+    assert relerr(pred.grad, pr.grad) < BF16_TOL
+    assert float(pred.grad[~mask].abs().max()) == 0.0      # visible tokens get exactly zero gradient
+
+
+def test_masked_mse_all_visible_is_zero_not_nan(env):
+    ops, L, dev, g = env
+    clip = torch.randn(1, 3, 2, 16, 16, device=dev, generator=g)
+    pred = torch.randn(1, 8, 192, device=dev, generator=g).bfloat16()
+    loss = ops.masked_mse(pred, clip, torch.zeros(1, 8, dtype=torch.bool, device=dev), 1, 8, 1)
+    assert float(loss) == 0.0
+
+
+def test_mask_indices_gather_scatter(env):
+    ops, L, dev, g = env
+    B, T, S, pt, ps, D, n_vis = 3, 4, 64, 2, 16, 384, 3
+    Tp, Lp = T // pt, (S // ps) ** 2
+    frame = torch.ones(B, Lp, device=dev, dtype=torch.bool)
+    for b in range(B):
+        frame[b, torch.randperm(Lp, device=dev, generator=g)[:n_vis]] = False
+    vis = ops.mask_to_indices(frame.to(torch.uint8), n_vis)
+    ref_vis = torch.stack([torch.nonzero(~frame[b]).flatten() for b in range(B)])
+    assert torch.equal(vis.long(), ref_vis)                 # gather indices: bit-exact
+    clip = torch.randn(B, 3, T, S, S, device=dev, generator=g)
+    tpos = torch.randn(1, Tp, 1, D, device=dev, generator=g, requires_grad=True)
+    spos = torch.randn(1, 1, Lp, D, device=dev, generator=g, requires_grad=True)
+    patches, pos_rows = ops.TubeletGatherFn.apply(clip, vis, tpos, spos, pt, ps)
+    K = 3 * pt * ps * ps
+    u = clip.reshape(B, 3, Tp, pt, S // ps, ps, S // ps, ps).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B, Tp, Lp, K)
+    ref_p = torch.stack([u[b][:, ref_vis[b]] for b in range(B)]).reshape(-1, K)
+    assert relerr(patches, ref_p) < BF16_TOL
+    ref_pos = torch.stack([tpos[0, :, 0][:, None] + spos[0, 0][ref_vis[b]][None] for b in range(B)]).reshape(-1, D)
+    assert relerr(pos_rows, ref_pos) < 1e-6
+    gr = torch.randn_like(pos_rows)
+    pos_rows.backward(gr)
+    gt, gs = torch.autograd.grad(ref_pos, (tpos, spos), gr)
+    assert relerr(tpos.grad, gt) < 1e-4 and relerr(spos.grad, gs) < 1e-4
+    # decoder input: scatter + pos + mask token, forward and backward
+    mask_full = frame[:, None, :].expand(B, Tp, Lp).reshape(B, Tp * Lp).contiguous()
+    z = torch.randn(B * Tp * n_vis, D, device=dev, generator=g).bfloat16().requires_grad_(True)
+    tp2 = torch.randn(1, Tp, 1, D, device=dev, generator=g, requires_grad=True)
+    sp2 = torch.randn(1, 1, Lp, D, device=dev, generator=g, requires_grad=True)
+    mt = torch.randn(1, 1, D, device=dev, generator=g, requires_grad=True)
+    x_dec = ops.DecoderInputFn.apply(z, vis, mask_full.to(torch.uint8), tp2, sp2, mt, B, Tp, Lp)
+    full = torch.zeros(B, Tp, Lp, D, device=dev)
+    full = full.index_put((torch.arange(B, device=dev)[:, None, None], torch.arange(Tp, device=dev)[None, :, None], ref_vis[:, None, :]),
+                          z.float().reshape(B, Tp, n_vis, D))
+    m = mask_full.view(B, Tp, Lp, 1).float()
+    xr = ((full + (tp2 + sp2)) * (1 - m) + mt * m).reshape(B, Tp * Lp, D)
+    assert relerr(x_dec, xr) < 1e-6
+    gx = torch.randn_like(x_dec)
+    refs = torch.autograd.grad(xr, (z, tp2, sp2, mt), gx)
+    x_dec.backward(gx)
+    assert relerr(z.grad, refs[0]) < BF16_TOL
+    for a, r in zip((tp2.grad, sp2.grad, mt.grad), refs[1:]):
+        assert relerr(a, r) < 1e-4
+
+
+def test_small_helpers(env):
+    ops, L, dev, g = env
+    dy = torch.randn(5000, 1536, device=dev, generator=g).bfloat16()
+    assert relerr(ops.colsum(dy), dy.float().sum(0)) < 1e-4
+    x = torch.randn(100003, device=dev, generator=g)
+    assert torch.equal(ops.cast_bf16(x), x.bfloat16()) and torch.equal(ops.cast_f32(x.bfloat16()), x.bfloat16().float())
+    y = torch.ones_like(x)
+    ops.scale_f32(x, 0.25, out=y, accumulate=True)
+    assert torch.equal(y, 1 + x * 0.25)                       # separate IEEE mul + add: bit-exact
+    pre = torch.randn(4096, device=dev, generator=g).bfloat16()
+    d = torch.randn(4096, device=dev, generator=g).bfloat16()
+    pf = pre.float().requires_grad_(True)
+    F.gelu(pf).backward(d.float())
+    assert relerr(ops.gelu_bwd(d, pre), pf.grad) < BF16_TOL
+
+
+def test_gaussian_noise_statistics_and_determinism(env):
+    from ssl_vit_video_analytics_b200.privacy.feature_noise import add_gaussian_noise
+
+    ops, L, dev, g = env
+    z = torch.randn(1 << 20, device=dev, generator=g)
+    a = ops.GaussianNoiseFn.apply(z, 0.1, 1234, 0)
+    b = ops.GaussianNoiseFn.apply(z, 0.1, 1234, 0)
+    c = ops.GaussianNoiseFn.apply(z, 0.1, 1235, 0)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    eps = (a - z) / 0.1
+    assert abs(float(eps.mean())) < 5e-3 and abs(float(eps.std()) - 1) < 5e-3 and abs(float((eps ** 4).mean()) - 3) < 0.05
+    zz = z[:1000].clone().requires_grad_(True)
+    out = add_gaussian_noise(zz, 0.2)
+    out.sum().backward()
+    assert torch.equal(zz.grad, torch.ones_like(zz)) and out is not zz
+    assert add_gaussian_noise(zz, 0.0) is zz
+
+
+def test_fedavg_aggregate_on_device_is_bit_exact_with_cpu(env):
+    import torch.nn as nn
+
+    from oracle import restatement as R
+    from ssl_vit_video_analytics_b200.federated.fed_loop import fedavg_aggregate
+
+    ops, L, dev, g = env
+    torch.manual_seed(0)
+    glob = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Flatten(), nn.Linear(8, 4)).to(dev)
+    clients = []
+    for i in range(5):
+        m = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Flatten(), nn.Linear(8, 4)).to(dev)
+        m[1].num_batches_tracked.fill_(i)
+        clients.append({k: v.detach().clone() for k, v in m.state_dict().items()})
+    w = [1907.0, 1893.0, 1921.0, 1880.0, 1936.0]
+    ref = R.fedavg({k: v.cpu() for k, v in glob.state_dict().items()}, [{k: v.cpu() for k, v in c.items()} for c in clients], w)
+    new = fedavg_aggregate(glob, clients, w)
+    for k in ref:
+        assert torch.equal(new[k], ref[k]), k
