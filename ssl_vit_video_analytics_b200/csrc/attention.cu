@@ -20,6 +20,11 @@ namespace vmae {
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 UMMA, warps 2..5 one thread per row
 constexpr float LOG2E = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2; exp2f() costs ~10 instructions (denormal handling)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -158,11 +163,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t r[32];
         tmem_ld32(tS + lane_off + c * 32, r);
         tmem_wait_ld();
+        if (valid == BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
-      const float alpha = exp2f((m - mx) * sl2);
+      const float alpha = ex2_approx((m - mx) * sl2);
       m = mx;
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -184,10 +194,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_ld32(tS + lane_off + c * 32, r);
         tmem_wait_ld();
         float p[32];
+        if (valid == BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          p[i] = (c * 32 + i < valid) ? exp2f(__uint_as_float(r[i]) * sl2 - msl) : 0.f;
-          l += p[i];
+          for (int i = 0; i < 32; ++i) {
+            p[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
+            l += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl)) : 0.f;
+            l += p[i];
+          }
         }
         store_tile_row32(sP, row, c * 32, p);
       }
@@ -407,7 +425,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
         for (int i = tid; i < 2 * BS; i += 128) {
           const int c = i % BS;
           const int g = it * BS + c;
-          float v = 0.f;
+          float v = (i < BS) ? INFINITY : 0.f;  // masked column: exp2(s - inf) == 0
           if (g < L) v = (i < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
           st_lse[i] = v;  // st_delta == st_lse + BS
         }
@@ -423,17 +441,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
         tmem_ld32(tT1 + lane_off + c * 32, rp);
         tmem_wait_ld();
         float ds[32], pp[32];
+        if (MODE == BWD_DQ) {
+          if (valid == BS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          float p;
-          if (MODE == BWD_DQ) {
-            p = (col < valid) ? exp2f(__uint_as_float(rs[i]) * sl2 - lse_row) : 0.f;
-            ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+            for (int i = 0; i < 32; ++i) {
+              const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row));
+              ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+            }
           } else {
-            p = (col < valid) ? exp2f(__uint_as_float(rs[i]) * sl2 - st_lse[col]) : 0.f;
-            ds[i] = p * (__uint_as_float(rp[i]) - st_delta[col]) * scale;
-            pp[i] = p;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float p = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row)) : 0.f;
+              ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+            }
+          }
+        } else {
+          // out-of-range query columns carry lse = +inf in the staged statistics, so p == 0 there without a predicate
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c * 32 + 4 * i4);
+            const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c * 32 + 4 * i4);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = 4 * i4 + t;
+              const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lv[t]));
+              ds[i] = p * (__uint_as_float(rp[i]) - dv[t]) * scale;
+              pp[i] = p;
+            }
           }
         }
         store_tile_row32(sE(0), row, c * 32, ds);

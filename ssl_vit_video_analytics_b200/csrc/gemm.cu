@@ -25,7 +25,8 @@ constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_SMEM_BUDGET = 193 * 1024;
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32x32 fp32 tile per epilogue warp
 
 struct GemmParams {
   int M, N, K;
@@ -52,14 +53,52 @@ struct GemmCfg {
   static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU evaluated without MUFU: Phi(x) = 0.5 + x * P(x^2) on |x| <= 4.2 (degree-8 minimax fit, max abs error
+// 1.6e-5 in fp32 Horner form, 1.3e-5 beyond the clamp) — two orders of magnitude below bf16 resolution of the outputs.
+__device__ __forceinline__ float normal_cdf(float x) {
+  const float xc = fminf(fmaxf(x, -4.2f), 4.2f);
+  const float u = xc * xc;
+  float p = 5.3164563029728384e-11f;
+  p = fmaf(p, u, -5.110036394029294e-09f);
+  p = fmaf(p, u, 2.1774354763692827e-07f);
+  p = fmaf(p, u, -5.478650564327836e-06f);
+  p = fmaf(p, u, 9.182147914543748e-05f);
+  p = fmaf(p, u, -0.0010986902052536607f);
+  p = fmaf(p, u, 0.00978302676230669f);
+  p = fmaf(p, u, -0.0662931576371193f);
+  p = fmaf(p, u, 0.3988766670227051f);
+  return fmaf(xc, p, 0.5f);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * normal_cdf(x); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  return fmaf(x, pdf, normal_cdf(x));
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_f4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  return u;
 }
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -69,7 +108,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = staging_base + GEMM_STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -192,11 +232,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ===================== epilogue warps =====================
+    // Per 32-column chunk: (1) TMEM -> registers (thread = row) -> warp-private swizzled fp32 staging tile in smem;
+    // (2) re-read with a coalesced mapping (8 lanes x float4 = one 128 B row segment, 4 rows per instruction) and run
+    // the whole epilogue (bias, GELU, gelu', residual, dtype conversion, store / red.add) on that mapping, so every
+    // global access touches full 64/128-byte row segments.
     const int ew = warp - 2;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
     const int half = ew >> 2;               // which half of the tile's columns
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
     constexpr int CHUNKS = COLS_PER_WARP / 32;
+    const uint32_t stage_tile = staging_base + ew * 4096;
+    const int c4 = lane & 7;                // float4 index inside the 32-column chunk
+    const int rsub = lane >> 3;             // row inside a group of 4
     int as = 0;
     uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -205,107 +252,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (kb0 >= kb1) continue;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = half * COLS_PER_WARP + c * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col0, r);
         tmem_wait_ld();
-        const int n = n0 + col0;
-        if (n >= p.N) continue;  // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
+        if (c == CHUNKS - 1) {
+          // every TMEM read of this accumulator stage has completed -> hand it back to the UMMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        if (!row_ok) continue;
-        if (p.act == 1) {
-          if (p.aux_out) {
-            __nv_bfloat16* dst = p.aux_out + static_cast<long long>(row) * p.ld_aux_out + n;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (n + j < p.N) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(dst + j) = pk;
-              }
-            }
+        for (int j = 0; j < 8; ++j)
+          st_shared_f4(stage_tile + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int n = n0 + col0 + c4 * 4;
+        const bool col_ok = n < p.N;    // N % 8 == 0 and n % 4 == 0: a float4 is either fully inside or fully outside
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + rsub;
+          float4 v = ld_shared_f4(stage_tile + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+          const int row = m0 + quad * 32 + rl;
+          if (!col_ok || row >= p.M) continue;
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          const long long ro = static_cast<long long>(row);
+          if (p.act == 1) {
+            if (p.aux_out) *reinterpret_cast<uint2*>(p.aux_out + ro * p.ld_aux_out + n) = pack_bf16x4(v);
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (p.aux_in) {
-          const __nv_bfloat16* src = p.aux_in + static_cast<long long>(row) * p.ld_aux_in + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j < p.N) {
-              const uint4 pk = __ldg(reinterpret_cast<const uint4*>(src + j));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __bfloat1622float2(h2[t]);
-                v[j + 2 * t] *= gelu_erf_grad(f.x);
-                v[j + 2 * t + 1] *= gelu_erf_grad(f.y);
-              }
-            }
+          if (p.aux_in) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.aux_in + ro * p.ld_aux_in + n));
+            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            v.x *= gelu_erf_grad(h0.x); v.y *= gelu_erf_grad(h0.y); v.z *= gelu_erf_grad(h1.x); v.w *= gelu_erf_grad(h1.y);
           }
-        }
-        if (p.residual) {
-          const float* src = p.residual + static_cast<long long>(row) * p.ld_res + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j < p.N) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(src + j));
-              v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-            }
+          if (p.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + ro * p.ld_res + n));
+            v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
           }
-        }
-        if (p.out_fp32) {
-          float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ld_out + n;
-          if (p.atomic_add) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) atomicAdd(dst + j, v[j]);
+          if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.out) + ro * p.ld_out + n;
+            if (p.atomic_add) red_add_f4(dst, v);
+            else *reinterpret_cast<float4*>(dst) = v;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (n + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ld_out + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j < p.N) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ro * p.ld_out + n) = pack_bf16x4(v);
           }
         }
+        __syncwarp();  // staging tile is reused by the next chunk
       }
-      // all TMEM reads of this accumulator stage are complete (wait::ld above) -> hand it back to the UMMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

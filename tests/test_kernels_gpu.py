@@ -21,7 +21,7 @@ def env():
 
 
 def relerr(got, ref):
-    got, ref = got.float(), ref.float()
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
     assert torch.isfinite(got).all()
     return float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
 

@@ -96,37 +96,47 @@ def mode_mnmn():
     return ok
 
 
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def mode_perf():
     g = torch.Generator(device="cuda").manual_seed(3)
     peak = 1644.1
-    for (M, N, K, tag) in [(100352, 1536, 384, "dec fc1"), (100352, 384, 1536, "dec fc2"), (100352, 1152, 384, "dec qkv"),
-                           (100352, 384, 384, "dec proj"), (10240, 1536, 384, "enc fc1"), (8192, 8192, 8192, "square")]:
+    M = 100352
+    for (N, K, tag) in [(1536, 384, "fc1"), (384, 1536, "fc2"), (1152, 384, "qkv"), (384, 384, "proj")]:
         x = torch.randn(M, K, device=dev, generator=g).bfloat16()
         w = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+        b = torch.randn(N, device=dev, generator=g)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            gemm(x, K, 0, w, K, 0, M, N, K, out=out)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        iters = 10
-        for _ in range(iters):
-            gemm(x, K, 0, w, K, 0, M, N, K, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        tf = 2.0 * M * N * K / ms / 1e9
-        gb = (M * K + N * K + M * N) * 2 / ms / 1e6
-        for _ in range(3):
-            torch.matmul(x, w.t(), out=out)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            torch.matmul(x, w.t(), out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / iters
-        print(f"perf {tag} {M}x{N}x{K}: ours {ms*1e3:.1f} us {tf:.0f} TF/s ({tf/peak*100:.1f}% of measured peak) {gb:.0f} GB/s | cuBLAS {ms2*1e3:.1f} us {2.0*M*N*K/ms2/1e9:.0f} TF/s", flush=True)
+        o32 = torch.empty(M, N, device=dev, dtype=torch.float32)
+        res = torch.randn(M, N, device=dev, generator=g)
+        pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        fl = 2.0 * M * N * K
+        rows = []
+        rows.append(("plain", _time(lambda: gemm(x, K, 0, w, K, 0, M, N, K, out=out))))
+        rows.append(("bias", _time(lambda: gemm(x, K, 0, w, K, 0, M, N, K, bias=b, out=out))))
+        rows.append(("bias+gelu+pre", _time(lambda: gemm(x, K, 0, w, K, 0, M, N, K, bias=b, aux_out=pre, out=out, act=1))))
+        rows.append(("bias+resid(f32)", _time(lambda: gemm(x, K, 0, w, K, 0, M, N, K, bias=b, residual=res, out=o32, out_fp32=True))))
+        rows.append(("dgelu(aux_in)", _time(lambda: gemm(x, K, 0, w, K, 0, M, N, K, aux_in=pre, out=out))))
+        rows.append(("cuBLAS", _time(lambda: torch.matmul(x, w.t(), out=out))))
+        # dgrad: dy [M,N] @ W [N,K] -> [M,K]
+        dy = torch.randn(M, N, device=dev, generator=g).bfloat16()
+        dx = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+        rows.append(("dgrad", _time(lambda: gemm(dy, N, 0, w, K, 1, M, K, N, out=dx))))
+        dw = torch.zeros(N, K, device=dev, dtype=torch.float32)
+        for ks in (4, 12, 24):
+            rows.append((f"wgrad ks={ks}", _time(lambda: gemm(dy, N, 1, x, K, 1, N, K, M, out=dw, out_fp32=True, accumulate=True, k_splits=ks))))
+        print(f"perf {tag} M={M} N={N} K={K}: " + " | ".join(f"{n} {ms*1e3:.0f}us {fl/ms/1e9:.0f}TF" for n, ms in rows), flush=True)
     return True
 
 
