@@ -52,6 +52,8 @@ int num_sms();  // cached multiprocessor count of the current device
 
 // Build a tiled TMA descriptor over a bf16 tensor. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
 // swizzle_bytes: 0, 64 or 128; the inner box extent in bytes must not exceed it.
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int swizzle_bytes);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes);
 

@@ -9,11 +9,17 @@
 // training GEMMs run from the tensors as they already sit in HBM, with no transposes:
 //   forward  y  = x  W^T : A = x  [M,K]  K-major,   B = W  [N,K]        K-major
 //   dgrad    dx = dy W   : A = dy [M,N'] K-major,   B = W  [N'(=K),K'(=N)] -> stored [Kc,N] = MN-major
-//   wgrad    dW = dy^T x : A = dy stored [Kc,M] = MN-major, B = x stored [Kc,N] = MN-major (split-K, fp32 atomics)
+//   wgrad    dW = dy^T x : A = dy stored [Kc,M] = MN-major, B = x stored [Kc,N] = MN-major (split-K, TMA reduce-add)
 //
 // Structure: persistent CTAs (grid = #SMs), 10 warps: warp0 = TMA producer, warp1 = UMMA issuer (+TMEM alloc),
 // warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns).
 // Pipelines: smem ring full/empty (TMA <-> UMMA), TMEM accumulator double buffer full/empty (UMMA <-> epilogue).
+//
+// Epilogue (per warp, per 32-column chunk): tcgen05.ld (thread = row) -> epilogue math in registers -> 16-byte stores
+// into a warp-private, hardware-swizzled staging box -> ONE TMA store (or TMA reduce-add) of the 32x32 box. Tensors the
+// epilogue reads (fp32 residual, bf16 pre-activation for gelu') arrive the same way: a TMA load of the next chunk's box
+// is in flight while the current chunk is processed. The threads therefore issue no global loads/stores at all; all
+// global traffic is full-line bulk copies and edge tiles are clipped by the TMA unit.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/vmae.h"
@@ -25,35 +31,46 @@ constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;
-constexpr int GEMM_SMEM_BUDGET = 193 * 1024;
-constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32x32 fp32 tile per epilogue warp
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
+
+enum : int {
+  EPI_BF16 = 0,        // out bf16 = acc (+bias)
+  EPI_BF16_GELU = 1,   // out bf16 = gelu(acc + bias), aux_out bf16 = acc + bias
+  EPI_BF16_DGELU = 2,  // out bf16 = acc * gelu'(aux_in)
+  EPI_F32 = 3,         // out f32  = acc (+bias)
+  EPI_F32_RESID = 4,   // out f32  = acc (+bias) + residual
+  EPI_F32_ACCUM = 5,   // out f32 += acc            (TMA reduce-add; split-K)
+};
+
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool OUT_F32 = (EPI == EPI_F32 || EPI == EPI_F32_RESID || EPI == EPI_F32_ACCUM);
+  static constexpr bool HAS_IN = (EPI == EPI_BF16_DGELU || EPI == EPI_F32_RESID);
+  static constexpr bool DUAL = (EPI == EPI_BF16_GELU);
+  static constexpr int BOX_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);     // one 32x32 staging box
+  static constexpr int BUF_BYTES = BOX_BYTES * (DUAL ? 2 : 1);     // per buffer (dual: activation + pre-activation)
+  static constexpr int WARP_BYTES = 2 * BUF_BYTES;                  // double buffered
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * WARP_BYTES;
+};
 
 struct GemmParams {
   int M, N, K;
   int k_splits;
-  const float* bias;            // [N] fp32 or null
-  const float* residual;        // [M, ld_res] fp32 or null  (added after activation)
-  long long ld_res;
-  const __nv_bfloat16* aux_in;  // [M, ld_aux_in] bf16 or null: multiply by gelu'(aux_in)
-  long long ld_aux_in;
-  __nv_bfloat16* aux_out;       // [M, ld_aux_out] bf16 or null: pre-activation copy (bias added)
-  long long ld_aux_out;
-  void* out;                    // bf16 or fp32 [M, ld_out]
-  long long ld_out;
-  int out_fp32;
-  int atomic_add;               // fp32 out only: red.add instead of store (split-K / gradient accumulation)
-  int act;                      // 0 none, 1 GELU(erf)
+  const float* bias;  // [N] fp32 or null
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int STAGING_BYTES = EpiTraits<EPI>::STAGING_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int AVAIL = GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES - 1024;
+  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static_assert(STAGES >= 2, "not enough shared memory for a double-buffered operand ring");
 };
 
 // Exact-erf GELU evaluated without MUFU: Phi(x) = 0.5 + x * P(x^2) on |x| <= 4.2 (degree-8 minimax fit, max abs error
@@ -72,51 +89,62 @@ __device__ __forceinline__ float normal_cdf(float x) {
   p = fmaf(p, u, 0.3988766670227051f);
   return fmaf(xc, p, 0.5f);
 }
-__device__ __forceinline__ float ex2_approx(float x) {
+__device__ __forceinline__ float ex2_approx_f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * normal_cdf(x); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float pdf = 0.39894228040143268f * ex2_approx_f(-0.72134752044448170f * x * x);  // exp(-x^2/2)
   return fmaf(x, pdf, normal_cdf(x));
 }
-__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_add_f4(float* addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
-__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a);
-  u.y = *reinterpret_cast<uint32_t*>(&b);
-  return u;
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
-template <int BLOCK_N, int A_MN, int B_MN>
+// Staging-box addressing (must match the TMA swizzle of the box's tensor map):
+//  fp32 box: 32 rows x 128 B, SWIZZLE_128B: 16-byte slot j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
+//  bf16 box: 32 rows x  64 B, SWIZZLE_64B : 16-byte slot j of row r lives at r*64  + ((j ^ ((r >> 1) & 3)) << 4)
+__device__ __forceinline__ uint32_t box_f32_slot(uint32_t box, int r, int j) { return box + r * 128 + ((j ^ (r & 7)) << 4); }
+__device__ __forceinline__ uint32_t box_bf16_slot(uint32_t box, int r, int j) { return box + r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
+template <int BLOCK_N, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, EPI>;
+  using ET = EpiTraits<EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = staging_base + GEMM_STAGING_BYTES;
+  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (18 + a); };
+  auto in_bar = [&](int w, int b) { return bar_base + 8u * (20 + 2 * w + b); };  // 16 barriers: epilogue-input boxes
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 40;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,12 +152,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  const int kb_per_split = (num_kb + p.k_splits - 1) / p.k_splits;
+  const int kb_per_split = (num_kb + p.k_splits - 1) / p.k_splits;  // host guarantees: no split is empty
   const int total_units = m_tiles * n_tiles * p.k_splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_out);
+    if (ET::HAS_IN || ET::DUAL) tma_prefetch_desc(&tma_aux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -137,6 +167,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
+    }
+    for (int w = 0; w < GEMM_EPI_WARPS; ++w) {
+      mbar_init(in_bar(w, 0), 1);
+      mbar_init(in_bar(w, 1), 1);
     }
     fence_mbar_init();
   }
@@ -203,7 +237,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         int m0, n0, kb0, kb1;
         decode(unit, m0, n0, kb0, kb1);
-        if (kb0 >= kb1) continue;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -232,31 +265,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ===================== epilogue warps =====================
-    // Per 32-column chunk: (1) TMEM -> registers (thread = row) -> warp-private swizzled fp32 staging tile in smem;
-    // (2) re-read with a coalesced mapping (8 lanes x float4 = one 128 B row segment, 4 rows per instruction) and run
-    // the whole epilogue (bias, GELU, gelu', residual, dtype conversion, store / red.add) on that mapping, so every
-    // global access touches full 64/128-byte row segments.
     const int ew = warp - 2;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
     const int half = ew >> 2;               // which half of the tile's columns
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
     constexpr int CHUNKS = COLS_PER_WARP / 32;
-    const uint32_t stage_tile = staging_base + ew * 4096;
-    const int c4 = lane & 7;                // float4 index inside the 32-column chunk
-    const int rsub = lane >> 3;             // row inside a group of 4
+    const uint32_t my_staging = staging_base + ew * ET::WARP_BYTES;
+    const int r = lane;                     // row inside the 32-row box
     int as = 0;
     uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    uint32_t item = 0;                      // running (unit, chunk) counter: selects the staging buffer and barrier phase
+
+    // coordinates of chunk c of a unit for this warp
+    auto chunk_coords = [&](int unit, int c, int& gm, int& gn) {
       int m0, n0, kb0, kb1;
       decode(unit, m0, n0, kb0, kb1);
-      if (kb0 >= kb1) continue;
+      gm = m0 + quad * 32;
+      gn = n0 + half * COLS_PER_WARP + c * 32;
+    };
+    if (ET::HAS_IN && lane == 0 && static_cast<int>(blockIdx.x) < total_units) {
+      int gm, gn;
+      chunk_coords(blockIdx.x, 0, gm, gn);
+      mbar_expect_tx(in_bar(ew, 0), ET::BOX_BYTES);
+      tma_load_2d(my_staging, &tma_aux, in_bar(ew, 0), gn, gm);
+    }
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = half * COLS_PER_WARP + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col0, r);
+      for (int c = 0; c < CHUNKS; ++c, ++item) {
+        const int b = item & 1;
+        const uint32_t buf = my_staging + b * ET::BUF_BYTES;
+        int gm, gn;
+        chunk_coords(unit, c, gm, gn);
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + half * COLS_PER_WARP + c * 32, acc);
         tmem_wait_ld();
         if (c == CHUNKS - 1) {
           // every TMEM read of this accumulator stage has completed -> hand it back to the UMMA warp early
@@ -264,50 +307,80 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st_shared_f4(stage_tile + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        __syncwarp();
-        const int n = n0 + col0 + c4 * 4;
-        const bool col_ok = n < p.N;    // N % 8 == 0 and n % 4 == 0: a float4 is either fully inside or fully outside
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        if (EPI != EPI_F32_ACCUM && EPI != EPI_BF16_DGELU && p.bias != nullptr) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rl = it * 4 + rsub;
-          float4 v = ld_shared_f4(stage_tile + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-          const int row = m0 + quad * 32 + rl;
-          if (!col_ok || row >= p.M) continue;
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          const long long ro = static_cast<long long>(row);
-          if (p.act == 1) {
-            if (p.aux_out) *reinterpret_cast<uint2*>(p.aux_out + ro * p.ld_aux_out + n) = pack_bf16x4(v);
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-          }
-          if (p.aux_in) {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.aux_in + ro * p.ld_aux_in + n));
-            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-            const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-            v.x *= gelu_erf_grad(h0.x); v.y *= gelu_erf_grad(h0.y); v.z *= gelu_erf_grad(h1.x); v.w *= gelu_erf_grad(h1.y);
-          }
-          if (p.residual) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + ro * p.ld_res + n));
-            v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-          }
-          if (p.out_fp32) {
-            float* dst = reinterpret_cast<float*>(p.out) + ro * p.ld_out + n;
-            if (p.atomic_add) red_add_f4(dst, v);
-            else *reinterpret_cast<float4*>(dst) = v;
-          } else {
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ro * p.ld_out + n) = pack_bf16x4(v);
+          for (int j = 0; j < 32; j += 4) {
+            if (gn + j < p.N) {  // N % 8 == 0: a float4 is either fully inside or fully outside
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
           }
         }
-        __syncwarp();  // staging tile is reused by the next chunk
+        if (ET::HAS_IN) mbar_wait(in_bar(ew, b), (item >> 1) & 1u);
+        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+          if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts_u4(box_bf16_slot(buf + ET::BOX_BYTES, r, j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                     pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts_u4(box_bf16_slot(buf, r, j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                   pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+        } else if (EPI == EPI_BF16_DGELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = box_bf16_slot(buf, r, j);
+            const uint4 h = lds_u4(a);
+            const float2 h0 = unpack2(h.x), h1 = unpack2(h.y), h2 = unpack2(h.z), h3 = unpack2(h.w);
+            sts_u4(a, pack2(v[8 * j] * gelu_erf_grad(h0.x), v[8 * j + 1] * gelu_erf_grad(h0.y)),
+                   pack2(v[8 * j + 2] * gelu_erf_grad(h1.x), v[8 * j + 3] * gelu_erf_grad(h1.y)),
+                   pack2(v[8 * j + 4] * gelu_erf_grad(h2.x), v[8 * j + 5] * gelu_erf_grad(h2.y)),
+                   pack2(v[8 * j + 6] * gelu_erf_grad(h3.x), v[8 * j + 7] * gelu_erf_grad(h3.y)));
+          }
+        } else if (EPI == EPI_F32_RESID) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = box_f32_slot(buf, r, j);
+            const float4 q = lds_f4(a);
+            sts_f4(a, v[4 * j] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z, v[4 * j + 3] + q.w);
+          }
+        } else {  // EPI_F32, EPI_F32_ACCUM
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts_f4(box_f32_slot(buf, r, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (EPI == EPI_F32_ACCUM) tma_reduce_add_2d(&tma_out, buf, gn, gm);
+          else tma_store_2d(&tma_out, buf, gn, gm);
+          if (EPI == EPI_BF16_GELU) tma_store_2d(&tma_aux, buf + ET::BOX_BYTES, gn, gm);
+          tma_store_commit();
+          tma_store_wait_read<1>();  // the other buffer (previous item) has been read out -> free for reuse
+          if (ET::HAS_IN) {
+            // prefetch the input box of the next item into the other buffer
+            int nunit = unit, nc = c + 1;
+            if (nc == CHUNKS) { nunit = unit + gridDim.x; nc = 0; }
+            if (nunit < total_units) {
+              int ngm, ngn;
+              chunk_coords(nunit, nc, ngm, ngn);
+              mbar_expect_tx(in_bar(ew, b ^ 1), ET::BOX_BYTES);
+              tma_load_2d(my_staging + (b ^ 1) * ET::BUF_BYTES, &tma_aux, in_bar(ew, b ^ 1), ngn, ngm);
+            }
+          }
+        }
+        __syncwarp();
       }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp have completed before the CTA retires
   }
 
   tc_fence_before();
@@ -318,23 +391,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+struct GemmMaps {
+  CUtensorMap a, b, out, aux;
+};
+
+template <int BLOCK_N, int A_MN, int B_MN, int EPI>
+static int launch_gemm(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, EPI>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(m.a, m.b, m.out, m.aux, p);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
 
-static int pick_block_n(int N, int b_mn) {
-  (void)b_mn;
-  const int cands[4] = {256, 192, 128, 64};
+template <int BLOCK_N, int EPI>
+static int dispatch_major(int a_major, int b_major, const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K) return launch_gemm<BLOCK_N, 0, 0, EPI>(m, p, grid, stream);
+  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_MN) return launch_gemm<BLOCK_N, 0, 1, EPI>(m, p, grid, stream);
+  return launch_gemm<BLOCK_N, 1, 1, EPI>(m, p, grid, stream);
+}
+
+template <int BLOCK_N>
+static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BF16: return dispatch_major<BLOCK_N, EPI_BF16>(a_major, b_major, m, p, grid, stream);
+    case EPI_BF16_GELU: return dispatch_major<BLOCK_N, EPI_BF16_GELU>(a_major, b_major, m, p, grid, stream);
+    case EPI_BF16_DGELU: return dispatch_major<BLOCK_N, EPI_BF16_DGELU>(a_major, b_major, m, p, grid, stream);
+    case EPI_F32: return dispatch_major<BLOCK_N, EPI_F32>(a_major, b_major, m, p, grid, stream);
+    case EPI_F32_RESID: return dispatch_major<BLOCK_N, EPI_F32_RESID>(a_major, b_major, m, p, grid, stream);
+    default: return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
+  }
+}
+
+static int pick_block_n(int N) {
+  const int cands[3] = {256, 192, 128};
   for (int c : cands)
     if (N % c == 0) return c;
   // no exact fit: minimise padded columns, prefer the larger tile on ties
@@ -344,6 +439,14 @@ static int pick_block_n(int N, int b_mn) {
     if (waste < best_waste) { best = c; best_waste = waste; }
   }
   return best;
+}
+
+static int make_box_map(CUtensorMap* m, const void* base, int dtype, int M, int N, long long ld) {
+  const int es = dtype == VMAE_DTYPE_F32 ? 4 : 2;
+  const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+  const uint64_t str[1] = {(uint64_t)ld * es};
+  const uint32_t box[2] = {32, 32};
+  return make_tmap(m, base, dtype, 2, dims, str, box, 32 * es);
 }
 
 }  // namespace vmae
@@ -366,11 +469,30 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
   VMAE_CHECK_ARG(act == VMAE_ACT_NONE || act == VMAE_ACT_GELU, "vmae_gemm_bf16: bad act %d", act);
   if (k_splits < 1) k_splits = 1;
   VMAE_CHECK_ARG(k_splits == 1 || accumulate, "vmae_gemm_bf16: split-K needs accumulate=1");
-  VMAE_CHECK_ARG(k_splits == 1 || (!bias && !residual && !aux_in && !aux_out && act == VMAE_ACT_NONE),
-                 "vmae_gemm_bf16: split-K supports only the plain accumulate epilogue");
+  VMAE_CHECK_ARG(!accumulate || (!bias && !residual && !aux_in && !aux_out && act == VMAE_ACT_NONE),
+                 "vmae_gemm_bf16: accumulate supports only the plain epilogue");
   VMAE_CHECK_ARG(ld_out % (out_dtype == VMAE_DTYPE_F32 ? 4 : 8) == 0, "vmae_gemm_bf16: ld_out misaligned");
 
-  const int block_n = pick_block_n(N, b_major);
+  // epilogue selection (the fused combinations the training step uses; anything else is refused, never emulated)
+  int epi;
+  if (accumulate) {
+    epi = EPI_F32_ACCUM;
+  } else if (act == VMAE_ACT_GELU) {
+    VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && aux_out && !residual && !aux_in,
+                   "vmae_gemm_bf16: act=GELU needs bf16 output with aux_out (pre-activation) and no residual/aux_in");
+    epi = EPI_BF16_GELU;
+  } else if (aux_in) {
+    VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && !residual && !aux_out && !bias, "vmae_gemm_bf16: aux_in (gelu') needs a plain bf16 output");
+    epi = EPI_BF16_DGELU;
+  } else if (residual) {
+    VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_F32 && !aux_out, "vmae_gemm_bf16: residual needs fp32 output");
+    epi = EPI_F32_RESID;
+  } else {
+    VMAE_CHECK_ARG(!aux_out, "vmae_gemm_bf16: aux_out without act=GELU");
+    epi = out_dtype == VMAE_DTYPE_F32 ? EPI_F32 : EPI_BF16;
+  }
+
+  const int block_n = pick_block_n(N);
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   if (k_splits > num_kb) k_splits = num_kb;
   {  // no empty splits
@@ -378,54 +500,51 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
     k_splits = (num_kb + per - 1) / per;
   }
 
-  CUtensorMap ta, tb;
+  GemmMaps maps;
   int rc;
   if (a_major == VMAE_MAJOR_K) {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)lda * 2};
     const uint32_t box[2] = {64, (uint32_t)GEMM_BLOCK_M};
-    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, 128);
+    rc = make_tmap_bf16(&maps.a, A, 2, dims, str, box, 128);
   } else {
     const uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};
     const uint64_t str[1] = {(uint64_t)lda * 2};
     const uint32_t box[2] = {64, 64};
-    rc = make_tmap_bf16(&ta, A, 2, dims, str, box, 128);
+    rc = make_tmap_bf16(&maps.a, A, 2, dims, str, box, 128);
   }
   if (rc) return rc;
   if (b_major == VMAE_MAJOR_K) {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)ldb * 2};
     const uint32_t box[2] = {64, (uint32_t)block_n};
-    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
+    rc = make_tmap_bf16(&maps.b, B, 2, dims, str, box, 128);
   } else {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
     const uint64_t str[1] = {(uint64_t)ldb * 2};
     const uint32_t box[2] = {64, 64};
-    rc = make_tmap_bf16(&tb, B, 2, dims, str, box, 128);
+    rc = make_tmap_bf16(&maps.b, B, 2, dims, str, box, 128);
   }
+  if (rc) return rc;
+  rc = make_box_map(&maps.out, out, out_dtype, M, N, ld_out);
+  if (rc) return rc;
+  maps.aux = maps.out;
+  if (epi == EPI_BF16_GELU) rc = make_box_map(&maps.aux, aux_out, VMAE_DTYPE_BF16, M, N, ld_aux_out);
+  else if (epi == EPI_BF16_DGELU) rc = make_box_map(&maps.aux, aux_in, VMAE_DTYPE_BF16, M, N, ld_aux_in);
+  else if (epi == EPI_F32_RESID) rc = make_box_map(&maps.aux, residual, VMAE_DTYPE_F32, M, N, ld_res);
   if (rc) return rc;
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.k_splits = k_splits;
-  p.bias = bias; p.residual = residual; p.ld_res = ld_res;
-  p.aux_in = reinterpret_cast<const __nv_bfloat16*>(aux_in); p.ld_aux_in = ld_aux_in;
-  p.aux_out = reinterpret_cast<__nv_bfloat16*>(aux_out); p.ld_aux_out = ld_aux_out;
-  p.out = out; p.ld_out = ld_out; p.out_fp32 = (out_dtype == VMAE_DTYPE_F32); p.atomic_add = accumulate; p.act = act;
+  p.bias = bias;
 
   const int m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (N + block_n - 1) / block_n;
   const long long units = (long long)m_tiles * n_tiles * k_splits;
   const int grid = (int)(units < num_sms() ? units : num_sms());
-
-#define VMAE_GEMM_DISPATCH(BN)                                                                    \
-  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K) return launch_gemm<BN, 0, 0>(ta, tb, p, grid, stream); \
-  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_MN) return launch_gemm<BN, 0, 1>(ta, tb, p, grid, stream); \
-  return launch_gemm<BN, 1, 1>(ta, tb, p, grid, stream);
   switch (block_n) {
-    case 256: VMAE_GEMM_DISPATCH(256)
-    case 192: VMAE_GEMM_DISPATCH(192)
-    case 128: VMAE_GEMM_DISPATCH(128)
-    default: VMAE_GEMM_DISPATCH(64)
+    case 256: return dispatch_epi<256>(epi, a_major, b_major, maps, p, grid, stream);
+    case 192: return dispatch_epi<192>(epi, a_major, b_major, maps, p, grid, stream);
+    default: return dispatch_epi<128>(epi, a_major, b_major, maps, p, grid, stream);
   }
-#undef VMAE_GEMM_DISPATCH
 }
