@@ -8,7 +8,7 @@
 // K-major 128B-swizzle layout, and a second UMMA consumes those tiles. Two CTAs are co-resident per SM so one CTA's
 // exp/elementwise phase overlaps the other's tensor-core phase.
 //
-//   forward : S = Q K^T -> online softmax -> P (smem) -> O_j = P V_j (TMEM) -> rescale-accumulate in registers
+//   forward : S = Q K^T -> online softmax -> P (smem) -> O += P V_j accumulated in TMEM (lazy rescale on max growth)
 //   dQ      : S = Q K^T, dP = dO V^T -> dS = P*(dP - delta)*scale (smem) -> dQ += dS K          (TMEM accumulate)
 //   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem) -> dV += P^T dO, dK += dS^T Q      (TMEM accumulate)
 #include "common.cuh"
@@ -139,7 +139,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
           umma_bf16(tO, umma_smem_desc(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
-                    umma_smem_desc(sV(s) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_o, kk > 0);
+                    umma_smem_desc(sV(s) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_o, (j > 0 || kk > 0));
         umma_commit(o_full);
         umma_commit(kv_empty(s));
       }
@@ -149,15 +149,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float sl2 = scale * LOG2E;
+    // Online softmax with a lazily updated reference maximum: O accumulates in TMEM across all KV blocks and is only
+    // rescaled (TMEM -> registers -> TMEM) when some row of the warp sees its maximum grow by more than 2^8; otherwise the
+    // stale reference is kept (P <= 256 stays exact enough in bf16 and l / O carry the same factor, which cancels).
     float m = -INFINITY, l = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);   // S_j done  =>  PV_{j-1} done (UMMAs retire in issue order): O is stable, sP is free
       tc_fence_after();
       const int valid = min(BKV, L - j * BKV);
-      float mx = m;
+      float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t r[32];
@@ -172,21 +172,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      const float alpha = ex2_approx((m - mx) * sl2);
-      m = mx;
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      if (j == 0) {
+        m = mx;
+      } else {
+        const bool need = (mx - m) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m;
+          const float alpha = ex2_approx((m - m_new) * sl2);  // exactly 1 for rows that keep their reference
+          m = m_new;
+          l *= alpha;
 #pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tO + lane_off + c * 32, r);
-          tmem_wait_ld();
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tO + lane_off + c * 32, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tO + lane_off + c * 32, r);
+          }
+          tmem_wait_st();
         }
       }
-      l *= alpha;
       const float msl = m * sl2;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
@@ -227,10 +233,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;
-          pk.x = pack_bf16x2((o[c * 32 + i] + __uint_as_float(r[i])) * inv_l, (o[c * 32 + i + 1] + __uint_as_float(r[i + 1])) * inv_l);
-          pk.y = pack_bf16x2((o[c * 32 + i + 2] + __uint_as_float(r[i + 2])) * inv_l, (o[c * 32 + i + 3] + __uint_as_float(r[i + 3])) * inv_l);
-          pk.z = pack_bf16x2((o[c * 32 + i + 4] + __uint_as_float(r[i + 4])) * inv_l, (o[c * 32 + i + 5] + __uint_as_float(r[i + 5])) * inv_l);
-          pk.w = pack_bf16x2((o[c * 32 + i + 6] + __uint_as_float(r[i + 6])) * inv_l, (o[c * 32 + i + 7] + __uint_as_float(r[i + 7])) * inv_l);
+          pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
+          pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+          pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
+          pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
           *reinterpret_cast<uint4*>(dst + i) = pk;
         }
       }
@@ -446,13 +452,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row));
-              ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+              ds[i] = p * (__uint_as_float(rp[i]) - delta_row);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float p = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row)) : 0.f;
-              ds[i] = p * (__uint_as_float(rp[i]) - delta_row) * scale;
+              ds[i] = p * (__uint_as_float(rp[i]) - delta_row);
             }
           }
         } else {
@@ -467,7 +473,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
             for (int t = 0; t < 4; ++t) {
               const int i = 4 * i4 + t;
               const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lv[t]));
-              ds[i] = p * (__uint_as_float(rp[i]) - dv[t]) * scale;
+              ds[i] = p * (__uint_as_float(rp[i]) - dv[t]);
               pp[i] = p;
             }
           }
@@ -497,10 +503,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            pk.z = pack_bf16x2(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-            pk.w = pack_bf16x2(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            // dS was accumulated without the softmax scale; ACC1 of the dK/dV mode is dV = P^T dO (no scale)
+            const float f = (MODE == BWD_DKDV && a == 1) ? 1.0f : scale;
+            pk.x = pack_bf16x2(__uint_as_float(r[i]) * f, __uint_as_float(r[i + 1]) * f);
+            pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * f, __uint_as_float(r[i + 3]) * f);
+            pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * f, __uint_as_float(r[i + 5]) * f);
+            pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * f, __uint_as_float(r[i + 7]) * f);
             *reinterpret_cast<uint4*>(dst + i) = pk;
           }
         }

@@ -380,7 +380,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
                            float* dx_out, void* dx_out_bf16, float* dgamma, float* dbeta, long long rows, int cols, cudaStream_t s) {
   const int nv = (cols + 127) / 128;
   long long g = (rows + EW_WARPS - 1) / EW_WARPS;
-  const long long cap = (long long)num_sms() * 4;
+  const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
   const size_t smem = (size_t)EW_WARPS * 2 * cols * sizeof(float);
 #define LN_CASE(NV)                                                                                                      \

@@ -57,15 +57,34 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 // Wait with a watchdog: a pipeline bug becomes a trapped launch (CUDA error) instead of a hung GPU.
+// The hot path is a 4-instruction PTX spin (try_wait suspends in hardware); the timer is read once per 2048 spins, so
+// waiting warps leave the issue slots to the warps that compute.
 #ifndef VMAE_WATCHDOG_NS
 #define VMAE_WATCHDOG_NS 4000000000ull
 #endif
+__device__ __forceinline__ uint32_t mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "VMAE_SPIN_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra VMAE_DONE_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 2048;\n\t"
+      "@q bra VMAE_SPIN_%=;\n"
+      "VMAE_DONE_%=:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_spin(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0xffu) == 0u && globaltimer_ns() - t0 > VMAE_WATCHDOG_NS) {
+  while (!mbar_spin(bar, parity)) {
+    if (globaltimer_ns() - t0 > VMAE_WATCHDOG_NS) {
       printf("vmae: mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
@@ -163,6 +182,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {

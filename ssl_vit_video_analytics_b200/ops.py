@@ -370,6 +370,10 @@ def attention(qkv, num_heads):
     return AttentionFn.apply(qkv, num_heads)
 
 
+# (TensorImpl id, fp32 stream gradient, its bf16 copy) handed from one block's backward to the next one's
+_GRAD_SHADOW = [None]
+
+
 class TransformerBlockFn(torch.autograd.Function):
     """One pre-LN transformer block, forward and backward as a fixed schedule of fused kernels:
 
@@ -409,7 +413,10 @@ class TransformerBlockFn(torch.autograd.Function):
         (x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2) = ctx.saved_tensors
         B, Lq, H, hd = ctx.dims
         dx2 = dx2.contiguous()
-        dx2_b = cast_bf16(dx2)
+        # the LayerNorm backward of the block that produced dx2 already wrote a bf16 copy of it (same kernel, no extra read)
+        sh = _GRAD_SHADOW[0]
+        dx2_b = sh[2] if (sh is not None and sh[0] == dx2._cdata) else cast_bf16(dx2)
+        _GRAD_SHADOW[0] = None
         # ---- MLP branch
         dh = linear_dgrad(dx2_b, w2, aux_in=h_pre)          # d(fc1 out) = (dx2 W2) * gelu'(h_pre)
         dw2 = linear_wgrad(dx2_b, act)
@@ -426,7 +433,8 @@ class TransformerBlockFn(torch.autograd.Function):
         dln1 = linear_dgrad(dqkv, wq)
         dwq = linear_wgrad(dqkv, ln1)
         dbq = colsum(dqkv)
-        dx, _, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1)
+        dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, want_bf16=True)
+        _GRAD_SHADOW[0] = (dx._cdata, dx, dx_b)  # strong refs: the TensorImpl cannot be recycled while the entry lives
         return dx, dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2, None, None, None
 
 
