@@ -96,7 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tma_prefetch_desc(&map_kv);
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 4);
     mbar_init(o_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
@@ -124,22 +124,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
+      // descriptor bases are built once; inside the loops only the 14-bit start-address field advances (bytes >> 4).
+      // (Building a descriptor costs ~15 dependent ALU ops; with 32-cycle UMMAs that issue cost would dominate.)
+      const uint64_t dQ = umma_smem_desc(sQ, 0, 8 * Cfg::ROWB, Cfg::ROWB);
+      const uint64_t dK[2] = {umma_smem_desc(sK(0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sK(1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
+      const uint64_t dV[2] = {umma_smem_desc(sV(0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sV(1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
+      const uint64_t dP = umma_smem_desc(sP, 0, 1024, 128);
+      auto issue_s = [&](int j) {
         const int s = j & 1;
         mbar_wait(kv_full(s), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
-                    umma_smem_desc(sK(s) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_s, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, dQ + 2 * k, dK[s] + 2 * k, idesc_s, k > 0);
         umma_commit(s_full);
-        mbar_wait(p_ready, j & 1);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_ready, j & 1);   // rows have consumed S_j and written P_j
         tc_fence_after();
+        if (j + 1 < nkv) issue_s(j + 1);  // next scores first: the rows get S_{j+1} while P_j V_j is still being issued
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16(tO, umma_smem_desc(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
-                    umma_smem_desc(sV(s) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_o, (j > 0 || kk > 0));
+          umma_bf16(tO, dP + ((kk >> 2) * (128 * 128) + (kk & 3) * 32) / 16, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
         umma_commit(o_full);
         umma_commit(kv_empty(s));
       }
@@ -154,7 +162,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // stale reference is kept (P <= 256 stays exact enough in bf16 and l / O carry the same factor, which cancels).
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);   // S_j done  =>  PV_{j-1} done (UMMAs retire in issue order): O is stable, sP is free
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int valid = min(BKV, L - j * BKV);
       float mx = -INFINITY;
@@ -171,6 +179,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
+      }
+      if (j > 0) {  // P_{j-1} V_{j-1} has retired: O is stable and sP may be overwritten
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
       }
       if (j == 0) {
         m = mx;
@@ -217,7 +229,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);   // one arrival per warp: mbarrier operations serialise
     }
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
@@ -333,7 +346,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
     tma_prefetch_desc(&map_str_do);
     mbar_init(res_full, 1);
     mbar_init(t_full, 1);
-    mbar_init(e_ready, 128);
+    mbar_init(e_ready, 4);
     mbar_init(e_free, 1);
     mbar_init(acc_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
@@ -373,36 +386,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
     if (elect_one()) {
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, BS, 0, 0);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);
-      mbar_wait(res_full, 0);
-      for (int it = 0; it < niter; ++it) {
+      // descriptor bases are built once; inside the loops only the 14-bit start-address field advances (bytes >> 4)
+      const uint64_t dR0 = umma_smem_desc(sR0, 0, 8 * Cfg::ROWB, Cfg::ROWB), dR1 = umma_smem_desc(sR1, 0, 8 * Cfg::ROWB, Cfg::ROWB);
+      const uint64_t dY0[2] = {umma_smem_desc(sY(0, 0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sY(1, 0), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
+      const uint64_t dY1[2] = {umma_smem_desc(sY(0, 1), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sY(1, 1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
+      const uint64_t dE0 = umma_smem_desc(sE(0), 0, 1024, 128), dE1 = umma_smem_desc(sE(1), 0, 1024, 128);
+      auto issue_t = [&](int it) {
         const int s = it & 1;
         mbar_wait(st_full(s), (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          umma_bf16(tT0, umma_smem_desc(sR0 + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
-                    umma_smem_desc(sY(s, 0) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_t, k > 0);
-        }
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tT0, dR0 + 2 * k, dY0[s] + 2 * k, idesc_t, k > 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          umma_bf16(tT1, umma_smem_desc(sR1 + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB),
-                    umma_smem_desc(sY(s, 1) + k * 32, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_t, k > 0);
-        }
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tT1, dR1 + 2 * k, dY1[s] + 2 * k, idesc_t, k > 0);
         umma_commit(t_full);
-        mbar_wait(e_ready, it & 1);
+      };
+      mbar_wait(res_full, 0);
+      issue_t(0);
+      for (int it = 0; it < niter; ++it) {
+        const int s = it & 1;
+        mbar_wait(e_ready, it & 1);   // rows have consumed T(it) and written E(it)
         tc_fence_after();
+        if (it + 1 < niter) issue_t(it + 1);  // next score tiles first: they are on the rows' critical path
 #pragma unroll
-        for (int kk = 0; kk < BS / 16; ++kk) {
-          // ACC0 += E0 * Y0 (Y0 read as an MN-major B operand: rows = contraction index, hd contiguous)
-          umma_bf16(tA0, umma_smem_desc(sE(0) + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
-                    umma_smem_desc(sY(s, 0) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_a, (it > 0 || kk > 0));
-        }
+        for (int kk = 0; kk < BS / 16; ++kk)  // ACC0 += E0 * Y0 (Y0 read as an MN-major B operand: rows = contraction index)
+          umma_bf16(tA0, dE0 + 2 * kk, dY0[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_a, (it > 0 || kk > 0));
         if (MODE == BWD_DKDV) {
 #pragma unroll
-          for (int kk = 0; kk < BS / 16; ++kk) {
-            umma_bf16(tA1, umma_smem_desc(sE(1) + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 0, 1024, 128),
-                      umma_smem_desc(sY(s, 1) + kk * 16 * Cfg::ROWB, 0, 8 * Cfg::ROWB, Cfg::ROWB), idesc_a, (it > 0 || kk > 0));
-          }
+          for (int kk = 0; kk < BS / 16; ++kk)
+            umma_bf16(tA1, dE1 + 2 * kk, dY1[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_a, (it > 0 || kk > 0));
         }
         umma_commit(st_empty(s));
         umma_commit(e_free);
@@ -422,20 +434,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
       lse_row = lse[stat_base + g_row] * LOG2E;
       delta_row = delta[stat_base + g_row];
     }
+    if (MODE == BWD_DKDV && tid < 2 * BS) {
+      const int g = tid % BS;
+      float v = (tid < BS) ? INFINITY : 0.f;
+      if (g < L) v = (tid < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
+      stat[tid] = v;
+    }
     for (int it = 0; it < niter; ++it) {
       const int valid = min(BS, L - it * BS);
       float* st_lse = stat + (it & 1) * 2 * BS;
       float* st_delta = st_lse + BS;
+      float stat_next = 0.f;
       if (MODE == BWD_DKDV) {
-        // column statistics of the streamed query block
-        for (int i = tid; i < 2 * BS; i += 128) {
-          const int c = i % BS;
-          const int g = it * BS + c;
-          float v = (i < BS) ? INFINITY : 0.f;  // masked column: exp2(s - inf) == 0
-          if (g < L) v = (i < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
-          st_lse[i] = v;  // st_delta == st_lse + BS
+        named_bar_sync(1, 128);   // statistics of this iteration (written during the previous one) are visible
+        // prefetch the column statistics of the NEXT streamed query block (global-load latency hidden behind this iteration);
+        // out-of-range columns get lse = +inf so that p == 0 there
+        if (tid < 2 * BS && it + 1 < niter) {
+          const int g = (it + 1) * BS + (tid % BS);
+          stat_next = (tid < BS) ? INFINITY : 0.f;
+          if (g < L) stat_next = (tid < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
         }
-        named_bar_sync(1, 128);
       }
       mbar_wait(t_full, it & 1);
       tc_fence_after();
@@ -481,9 +499,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
         store_tile_row32(sE(0), row, c * 32, ds);
         if (MODE == BWD_DKDV) store_tile_row32(sE(1), row, c * 32, pp);
       }
+      if (MODE == BWD_DKDV && tid < 2 * BS && it + 1 < niter) (stat + ((it + 1) & 1) * 2 * BS)[tid] = stat_next;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(e_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e_ready);   // one arrival per warp: mbarrier operations serialise
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
