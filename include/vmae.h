@@ -55,6 +55,12 @@ int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, lon
                    long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out, long long ld_out,
                    int out_dtype, int accumulate, int act, int k_splits, void* stream);
 
+/* Weight + bias gradient of y = x W^T + b in one launch (split-K, fp32 accumulation into existing buffers):
+ *   dw[n_out, k_in] += dy[tokens, n_out]^T x[tokens, k_in];   dbias[n_out] += column sums of dy (optional, may be NULL)
+ * The bias gradient costs one extra N=16 UMMA per K step against an all-ones tile (no second pass over dy). */
+int vmae_linear_wgrad(const void* dy, long long ld_dy, const void* x, long long ld_x, long long tokens, int n_out,
+                      int k_in, float* dw, long long ld_dw, float* dbias, int k_splits, void* stream);
+
 /* ---- K2: flash attention on tcgen05/TMEM (non-causal, no mask, no dropout) --------------------------------------
  * qkv: bf16 [B, L, 3, H, hd] (the packed projection output: q|k|v blocks, then head, then dim) — the layout of
  * Attention.qkv (tiny_vit.py:93,100) and of nn.MultiheadAttention.in_proj (mae_vit_adapter.py:40-48).

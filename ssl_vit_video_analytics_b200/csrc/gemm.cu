@@ -57,6 +57,7 @@ struct GemmParams {
   int M, N, K;
   int k_splits;
   const float* bias;  // [N] fp32 or null
+  float* bias_grad;   // EPI_F32_ACCUM only: [M] fp32, += sum over the contraction dimension of A (ones-column UMMA)
 };
 
 template <int BLOCK_N, int EPI>
@@ -66,10 +67,13 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = EpiTraits<EPI>::STAGING_BYTES;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int AVAIL = GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES - 1024;
+  static constexpr int ONES_BYTES = (EPI == EPI_F32_ACCUM) ? 2048 : 0;   // 16 x 64 bf16 tile of 1.0 (row-sum UMMA operand)
+  static constexpr int AVAIL = GEMM_SMEM_LIMIT - STAGING_BYTES - ONES_BYTES - BAR_BYTES - 1024;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int TMEM_NEED = 2 * BLOCK_N + ((EPI == EPI_F32_ACCUM) ? 32 : 0);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + ONES_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
+  static_assert(TMEM_NEED <= 512, "accumulating GEMMs use BLOCK_N <= 192 (room for the row-sum columns)");
   static_assert(STAGES >= 2, "not enough shared memory for a double-buffered operand ring");
 };
 
@@ -137,7 +141,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
+  const uint32_t ones_base = staging_base + Cfg::STAGING_BYTES;
+  const uint32_t bar_base = ones_base + Cfg::ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };
@@ -177,6 +182,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1) {
     tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (EPI == EPI_F32_ACCUM && warp == 2) {
+    // all-ones operand: layout-agnostic (every element is 1.0), so any valid descriptor over these 2 KB works
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sts_u4(ones_base + (lane * 4 + i) * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -254,6 +265,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
                                         : umma_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 2), 0, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (EPI == EPI_F32_ACCUM && p.bias_grad != nullptr && n0 == 0) {
+              // row sums of A over the contraction dimension = bias gradient: D2[128 x 16] += A * ones
+              constexpr uint32_t idesc_ones = umma_idesc_bf16(GEMM_BLOCK_M, 16, A_MN, 0);
+              umma_bf16(tmem_base + 2 * BLOCK_N + as * 16, adesc, umma_smem_desc_sw128(ones_base + k * (GEMM_UMMA_K * 2), 0, 1024),
+                        idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these UMMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -292,6 +309,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (EPI == EPI_F32_ACCUM && p.bias_grad != nullptr && half == 0) {
+        int m0, n0, kb0, kb1;
+        decode(unit, m0, n0, kb0, kb1);
+        if (n0 == 0) {
+          uint32_t rsum[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 2 * BLOCK_N + as * 16, rsum);
+          tmem_wait_ld();
+          const int row = m0 + quad * 32 + lane;
+          if (row < p.M) atomicAdd(p.bias_grad + row, __uint_as_float(rsum[0]));
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c, ++item) {
         const int b = item & 1;
@@ -424,12 +452,14 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
     case EPI_BF16_DGELU: return dispatch_major<BLOCK_N, EPI_BF16_DGELU>(a_major, b_major, m, p, grid, stream);
     case EPI_F32: return dispatch_major<BLOCK_N, EPI_F32>(a_major, b_major, m, p, grid, stream);
     case EPI_F32_RESID: return dispatch_major<BLOCK_N, EPI_F32_RESID>(a_major, b_major, m, p, grid, stream);
-    default: return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
+    default:
+      if constexpr (BLOCK_N <= 192) return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
+      else return fail(VMAE_ERR_UNSUPPORTED, "accumulating GEMM with BLOCK_N=256 is not instantiated");
   }
 }
 
-static int pick_block_n(int N) {
-  const int cands[3] = {256, 192, 128};
+static int pick_block_n(int N, bool accumulate) {
+  const int cands[3] = {accumulate ? 192 : 256, 192, 128};  // accumulating GEMMs keep 32 TMEM columns for the row sums
   for (int c : cands)
     if (N % c == 0) return c;
   // no exact fit: minimise padded columns, prefer the larger tile on ties
@@ -453,10 +483,10 @@ static int make_box_map(CUtensorMap* m, const void* base, int dtype, int M, int 
 
 using namespace vmae;
 
-extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
-                              int M, int N, int K, const float* bias, const float* residual, long long ld_res,
-                              const void* aux_in, long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out,
-                              long long ld_out, int out_dtype, int accumulate, int act, int k_splits, void* stream_) {
+static int gemm_impl(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
+                     int M, int N, int K, const float* bias, const float* residual, long long ld_res,
+                     const void* aux_in, long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out,
+                     long long ld_out, int out_dtype, int accumulate, int act, int k_splits, float* bias_grad, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VMAE_CHECK_ARG(A && B && out, "vmae_gemm_bf16: null operand");
   VMAE_CHECK_ARG(M > 0 && N > 0 && K > 0, "vmae_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -492,7 +522,7 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
     epi = out_dtype == VMAE_DTYPE_F32 ? EPI_F32 : EPI_BF16;
   }
 
-  const int block_n = pick_block_n(N);
+  const int block_n = pick_block_n(N, accumulate != 0);
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   if (k_splits > num_kb) k_splits = num_kb;
   {  // no empty splits
@@ -537,6 +567,7 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.k_splits = k_splits;
   p.bias = bias;
+  p.bias_grad = bias_grad;
 
   const int m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (N + block_n - 1) / block_n;
@@ -547,4 +578,19 @@ extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const v
     case 192: return dispatch_epi<192>(epi, a_major, b_major, maps, p, grid, stream);
     default: return dispatch_epi<128>(epi, a_major, b_major, maps, p, grid, stream);
   }
+}
+
+extern "C" int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
+                              int M, int N, int K, const float* bias, const float* residual, long long ld_res,
+                              const void* aux_in, long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out,
+                              long long ld_out, int out_dtype, int accumulate, int act, int k_splits, void* stream) {
+  return gemm_impl(A, lda, a_major, B, ldb, b_major, M, N, K, bias, residual, ld_res, aux_in, ld_aux_in, aux_out, ld_aux_out, out, ld_out,
+                   out_dtype, accumulate, act, k_splits, nullptr, stream);
+}
+
+extern "C" int vmae_linear_wgrad(const void* dy, long long ld_dy, const void* x, long long ld_x, long long tokens, int n_out, int k_in,
+                                 float* dw, long long ld_dw, float* dbias, int k_splits, void* stream) {
+  VMAE_CHECK_ARG(tokens > 0 && tokens < (1ll << 31), "vmae_linear_wgrad: bad token count %lld", tokens);
+  return gemm_impl(dy, ld_dy, VMAE_MAJOR_MN, x, ld_x, VMAE_MAJOR_MN, n_out, k_in, (int)tokens, nullptr, nullptr, 0, nullptr, 0, nullptr, 0,
+                   dw, ld_dw, VMAE_DTYPE_F32, 1, VMAE_ACT_NONE, k_splits, dbias, stream);
 }

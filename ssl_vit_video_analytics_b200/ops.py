@@ -139,6 +139,21 @@ def linear_wgrad(dy, x, dw=None):
     return dw
 
 
+def linear_wgrad_bias(dy, x, dw=None, db=None):
+    """dW[N,K] += dy^T x and db[N] += colsum(dy) in ONE launch (the bias gradient rides on an extra N=16 UMMA)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    if dw is None:
+        dw = torch.zeros((N, K), device=dy.device, dtype=F32)
+    if db is None:
+        db = torch.zeros((N,), device=dy.device, dtype=F32)
+    rc = _run("gemm_wgrad", 2.0 * M * N * K, lambda: L.load().vmae_linear_wgrad(
+        _p(dy), dy.stride(0), _p(x), x.stride(0), M, N, K, _p(dw), dw.stride(0), _p(db), _wgrad_splits(M, N, K), _stream()))
+    L.check(rc, "vmae_linear_wgrad")
+    _count()
+    return dw, db
+
+
 def colsum(dy, db=None):
     M, N = dy.shape
     if db is None:
@@ -373,6 +388,23 @@ def attention(qkv, num_heads):
 # (TensorImpl id, fp32 stream gradient, its bf16 copy) handed from one block's backward to the next one's
 _GRAD_SHADOW = [None]
 
+# When a parameter already owns a contiguous fp32 .grad (e.g. a view into a GradientBucketer bucket), the fused block
+# accumulates into it directly (TMA reduce-add / red.add) and returns None to autograd: no zero-filled temporary, no
+# extra "grad += new" pass. GRAD_READY_HOOK(param) replaces the post-accumulate hook autograd would have fired.
+GRAD_READY_HOOK = None
+
+
+def _direct_grad(p):
+    g = getattr(p, "grad", None)
+    if g is not None and g.dtype == F32 and g.is_contiguous() and g.shape == p.shape and g.is_cuda:
+        return g
+    return None
+
+
+def _grad_done(p):
+    if GRAD_READY_HOOK is not None:
+        GRAD_READY_HOOK(p)
+
 
 class TransformerBlockFn(torch.autograd.Function):
     """One pre-LN transformer block, forward and backward as a fixed schedule of fused kernels:
@@ -392,6 +424,7 @@ class TransformerBlockFn(torch.autograd.Function):
         D = x.shape[-1]
         assert x.dtype == F32 and x.is_contiguous() and x.shape[0] == B * Lq
         hd = D // num_heads
+        params = (ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b)
         f = lambda t: t.float().contiguous()
         ln1_w, ln1_b, ln2_w, ln2_b = f(ln1_w), f(ln1_b), f(ln2_w), f(ln2_b)
         qkv_b, proj_b, fc1_b, fc2_b = f(qkv_b), f(proj_b), f(fc1_b), f(fc2_b)
@@ -406,6 +439,7 @@ class TransformerBlockFn(torch.autograd.Function):
         x2 = linear_fwd(act, w2, fc2_b, residual=x1)
         ctx.save_for_backward(x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2)
         ctx.dims = (B, Lq, num_heads, hd)
+        ctx.params = params
         return x2
 
     @staticmethod
@@ -417,25 +451,32 @@ class TransformerBlockFn(torch.autograd.Function):
         sh = _GRAD_SHADOW[0]
         dx2_b = sh[2] if (sh is not None and sh[0] == dx2._cdata) else cast_bf16(dx2)
         _GRAD_SHADOW[0] = None
+        P = ctx.params  # ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b
+        tgt = [(_direct_grad(p) if ctx.needs_input_grad[i + 1] else None) for i, p in enumerate(P)]
+        (t_g1, t_b1, t_wq, t_bq, t_wp, t_bp, t_g2, t_b2, t_w1, t_bb1, t_w2, t_bb2) = tgt
         # ---- MLP branch
         dh = linear_dgrad(dx2_b, w2, aux_in=h_pre)          # d(fc1 out) = (dx2 W2) * gelu'(h_pre)
-        dw2 = linear_wgrad(dx2_b, act)
-        db2 = colsum(dx2_b)
+        dw2, db2 = linear_wgrad_bias(dx2_b, act, t_w2, t_bb2)
         dln2 = linear_dgrad(dh, w1)
-        dw1 = linear_wgrad(dh, ln2)
-        db1 = colsum(dh)
-        dx1, dx1_b, dg2, dbeta2 = layernorm_bwd(dln2, x1, ln2_w, mean2, rstd2, dx_resid=dx2, want_bf16=True)
+        dw1, db1 = linear_wgrad_bias(dh, ln2, t_w1, t_bb1)
+        dx1, dx1_b, dg2, dbeta2 = layernorm_bwd(dln2, x1, ln2_w, mean2, rstd2, dx_resid=dx2, dgamma=t_g2, dbeta=t_b2, want_bf16=True)
         # ---- attention branch
         do = linear_dgrad(dx1_b, wp)
-        dwp = linear_wgrad(dx1_b, o)
-        dbp = colsum(dx1_b)
+        dwp, dbp = linear_wgrad_bias(dx1_b, o, t_wp, t_bp)
         dqkv = attn_bwd(qkv, o, do, lse, B, Lq, H, hd)
         dln1 = linear_dgrad(dqkv, wq)
-        dwq = linear_wgrad(dqkv, ln1)
-        dbq = colsum(dqkv)
-        dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, want_bf16=True)
+        dwq, dbq = linear_wgrad_bias(dqkv, ln1, t_wq, t_bq)
+        dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, dgamma=t_g1, dbeta=t_b1, want_bf16=True)
         _GRAD_SHADOW[0] = (dx._cdata, dx, dx_b)  # strong refs: the TensorImpl cannot be recycled while the entry lives
-        return dx, dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2, None, None, None
+        grads = [dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2]
+        out = []
+        # reverse order ~ the order in which the gradients became final (fc2 first), so buckets close as early as possible
+        for i in reversed(range(12)):
+            if tgt[i] is not None:
+                _grad_done(P[i])
+        for i in range(12):
+            out.append(None if tgt[i] is not None else grads[i])
+        return (dx, *out, None, None, None)
 
 
 def transformer_block(x, ln1, qkv_w, qkv_b, proj, ln2, fc1, fc2, num_heads, B, Lq):

@@ -70,6 +70,11 @@ class GradientBucketer(nn.Module):
                 p.register_post_accumulate_grad_hook(self._on_grad_ready)
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.on_cuda else None
         self.launched = 0
+        if self.on_cuda:
+            # fused blocks that accumulate straight into the bucket views report completion through this hook
+            from . import ops
+
+            ops.GRAD_READY_HOOK = self._on_direct_grad
 
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, *args, **kwargs):
@@ -86,6 +91,10 @@ class GradientBucketer(nn.Module):
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
+
+    def _on_direct_grad(self, p):
+        if p in self._bucket_of:
+            self._on_grad_ready(p)
 
     def _launch(self, b: _Bucket):
         self.launched += 1

@@ -66,6 +66,18 @@ def test_gemm_wgrad_split_k_accumulates(env, T, Np, Kp):
     assert relerr(dw, dy.float().t() @ x.float() + 1.0) < 1e-4
 
 
+@pytest.mark.parametrize("T,Np,Kp", [(64, 128, 64), (4096, 1152, 384), (10240, 1536, 384), (3000, 384, 1536), (1000, 192, 384), (50, 64, 72)])
+def test_wgrad_with_fused_bias_gradient(env, T, Np, Kp):
+    ops, L, dev, g = env
+    dy = (torch.randn(T, Np, device=dev, generator=g) * 0.1).bfloat16()
+    x = torch.randn(T, Kp, device=dev, generator=g).bfloat16()
+    dw = torch.ones(Np, Kp, device=dev)
+    db = torch.full((Np,), 2.0, device=dev)
+    ops.linear_wgrad_bias(dy, x, dw, db)               # both accumulate into existing buffers
+    assert relerr(dw, dy.float().t() @ x.float() + 1.0) < 1e-4
+    assert relerr(db, dy.float().sum(0) + 2.0) < 1e-4
+
+
 def test_gemm_rejects_bad_arguments(env):
     ops, L, dev, g = env
     x = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)

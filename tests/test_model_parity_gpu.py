@@ -165,3 +165,28 @@ def test_videomae_vit_full_size_properties():
     assert float(loss) == pytest.approx(float(ref), rel=1e-4)
     loss.backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_second_backward_accumulates_directly_into_grad_buffers():
+    """With .grad already allocated the fused blocks add into it in place (TMA reduce-add) and return None to autograd:
+    a second backward of the same loss must exactly double every gradient, and the data-parallel hook must fire."""
+    from ssl_vit_video_analytics_b200 import ops
+
+    cfg = _small_b_cfg()
+    model, sd, clip, mask, vis_host = _run_model_b(cfg, B=2)
+    model = model.cuda().train()
+    clip_d, mask_d = clip.cuda(), mask.cuda()
+    vis = model.visible_indices(mask_d)
+    model.training_loss(clip_d, mask_d, vis).backward()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+    ptrs = {k: p.grad.data_ptr() for k, p in model.named_parameters()}
+    seen = []
+    ops.GRAD_READY_HOOK = lambda p: seen.append(p)
+    try:
+        model.training_loss(clip_d, mask_d, vis).backward()
+    finally:
+        ops.GRAD_READY_HOOK = None
+    assert len(seen) == 12 * (cfg["model"]["depth"] + cfg["model"]["decoder_depth"])
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == ptrs[k]
+        assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-3, atol=1e-6 + 2e-3 * float(g1[k].abs().max())), k
