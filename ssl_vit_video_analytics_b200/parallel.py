@@ -26,6 +26,7 @@ class _Bucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.pending = len(params)
+        self.fired = {}
         self.work = None
         self.event: Optional[torch.cuda.Event] = None
 
@@ -84,10 +85,14 @@ class GradientBucketer(nn.Module):
         for b in self.buckets:
             b.flat.zero_()
             b.pending = len(b.params)
+            b.fired = {}
             b.work = None
 
     def _on_grad_ready(self, p: nn.Parameter):
         b = self._bucket_of[p]
+        if b.fired.get(id(p), 0):
+            return  # already signalled this step (a fused block reported it directly and autograd's hook ran as well)
+        b.fired[id(p)] = 1
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
@@ -115,8 +120,11 @@ class GradientBucketer(nn.Module):
         """Make the averaged gradients visible to the compute stream (call once after backward)."""
         for b in self.buckets:
             if b.pending != 0:
-                raise RuntimeError("a gradient bucket was not completed by backward: a parameter received no gradient; "
-                                   "exclude it via GradientBucketer(exclude=...)")
+                names = {id(p): n for n, p in self.module.named_parameters()}
+                missing = [names.get(id(p), "?") for p in b.params if b.fired.get(id(p), 0) == 0]
+                raise RuntimeError(f"a gradient bucket was not completed by backward: a parameter received no gradient "
+                                   f"(missing {missing[:8]}); exclude parameters that never get a gradient via "
+                                   f"GradientBucketer(exclude=...)")
             if self.world == 1:
                 continue
             if self.on_cuda:
