@@ -8,7 +8,7 @@
 // K-major 128B-swizzle layout, and a second UMMA consumes those tiles. Two CTAs are co-resident per SM so one CTA's
 // exp/elementwise phase overlaps the other's tensor-core phase.
 //
-//   forward : S = Q K^T -> online softmax -> P (smem) -> O += P V_j accumulated in TMEM (lazy rescale on max growth)
+//   forward : S = Q K^T -> online softmax -> P (bf16, TMEM A-operand) -> O += P V_j accumulated in TMEM (lazy rescale)
 //   dQ      : S = Q K^T, dP = dO V^T -> dS = P*(dP - delta)*scale (smem) -> dQ += dS K          (TMEM accumulate)
 //   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem) -> dV += P^T dO, dK += dS^T Q      (TMEM accumulate)
 #include "common.cuh"
@@ -44,6 +44,14 @@ __device__ __forceinline__ void store_tile_row32(uint32_t tile, int r, int col0,
                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
   }
 }
+// Write 32 consecutive K-elements of this thread's row (TMEM lane) as a bf16 UMMA A-operand held in TMEM: 16 packed
+// 32-bit columns starting at column (element index / 2) of the operand region.
+__device__ __forceinline__ void store_tmem_operand32(uint32_t taddr, const float (&v)[32]) {
+  uint32_t u[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  tmem_st16(taddr, u);
+}
 __device__ __forceinline__ void check_smem_alignment(const void* p) {
   if (threadIdx.x == 0 && (smem_u32(p) & 1023u) != 0) {
     printf("vmae attention: dynamic shared memory base is not 1024-byte aligned\n");
@@ -59,14 +67,16 @@ struct FwdCfg {
   static constexpr int ROWB = HD * 2;  // bytes per operand row == swizzle width (64 or 128)
   static constexpr int Q_BYTES = 128 * ROWB;
   static constexpr int KV_BYTES = BKV * ROWB;
-  static constexpr int P_BYTES = 128 * BKV * 2;
+  static constexpr int NS = 3;                            // K/V ring depth
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;           // K[2]
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;      // V[2]
-  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;           // K[NS]
+  static constexpr int OFF_V = OFF_K + NS * KV_BYTES;     // V[NS]
+  static constexpr int OFF_BAR = OFF_V + NS * KV_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = (BKV + HD <= 128) ? 128 : 256;
+  // TMEM columns: S fp32 [0,BKV) | O fp32 [BKV, BKV+HD) | P bf16 A-operand (BKV/2 packed columns)
+  static constexpr int TMEM_NEED = BKV + HD + BKV / 2;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : 256;
+  static_assert(TMEM_NEED <= 256, "two CTAs per SM share the 512 TMEM columns");
 };
 
 template <int HD, int BKV>
@@ -77,15 +87,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   check_smem_alignment(smem_raw);
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t sQ = sbase + Cfg::OFF_Q, sP = sbase + Cfg::OFF_P;
+  constexpr int NS = Cfg::NS;
+  const uint32_t sQ = sbase + Cfg::OFF_Q;
   auto sK = [&](int s) { return sbase + Cfg::OFF_K + s * Cfg::KV_BYTES; };
   auto sV = [&](int s) { return sbase + Cfg::OFF_V + s * Cfg::KV_BYTES; };
   const uint32_t bar = sbase + Cfg::OFF_BAR;
   const uint32_t q_full = bar, s_full = bar + 8, p_ready = bar + 16, o_full = bar + 24;
   auto kv_full = [&](int s) { return bar + 32 + 8 * s; };
-  auto kv_empty = [&](int s) { return bar + 48 + 8 * s; };
-  const uint32_t tmem_ptr_addr = bar + 64;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 64);
+  auto kv_empty = [&](int s) { return bar + 64 + 8 * s; };
+  const uint32_t tmem_ptr_addr = bar + 96;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -98,7 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
     mbar_init(o_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -106,15 +117,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tS = tmem, tO = tmem + BKV;
+  const uint32_t tS = tmem, tO = tmem + BKV, tP = tmem + BKV + HD;   // P: bf16 A-operand, BKV/2 packed columns
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
       tma_load_3d(sQ, &map_q, q_full, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1u);
+        const int s = j % NS;
+        mbar_wait(kv_empty(s), ((j / NS) & 1) ^ 1u);
         mbar_expect_tx(kv_full(s), 2 * Cfg::KV_BYTES);
         tma_load_3d(sK(s), &map_kv, kv_full(s), (H + h) * HD, j * BKV, b);
         tma_load_3d(sV(s), &map_kv, kv_full(s), (2 * H + h) * HD, j * BKV, b);
@@ -127,12 +138,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // descriptor bases are built once; inside the loops only the 14-bit start-address field advances (bytes >> 4).
       // (Building a descriptor costs ~15 dependent ALU ops; with 32-cycle UMMAs that issue cost would dominate.)
       const uint64_t dQ = umma_smem_desc(sQ, 0, 8 * Cfg::ROWB, Cfg::ROWB);
-      const uint64_t dK[2] = {umma_smem_desc(sK(0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sK(1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
-      const uint64_t dV[2] = {umma_smem_desc(sV(0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sV(1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
-      const uint64_t dP = umma_smem_desc(sP, 0, 1024, 128);
+      uint64_t dK[NS], dV[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        dK[s] = umma_smem_desc(sK(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
+        dV[s] = umma_smem_desc(sV(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
+      }
       auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(kv_full(s), (j >> 1) & 1);
+        const int s = j % NS;
+        mbar_wait(kv_full(s), (j / NS) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, dQ + 2 * k, dK[s] + 2 * k, idesc_s, k > 0);
@@ -141,13 +155,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(p_ready, j & 1);   // rows have consumed S_j and written P_j
+        const int s = j % NS;
+        mbar_wait(p_ready, j & 1);   // rows have consumed S_j and written P_j (bf16, in TMEM)
         tc_fence_after();
         if (j + 1 < nkv) issue_s(j + 1);  // next scores first: the rows get S_{j+1} while P_j V_j is still being issued
+        // O += P_j V_j with P read straight from TMEM (TS form): P never touches shared memory
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16(tO, dP + ((kk >> 2) * (128 * 128) + (kk & 3) * 32) / 16, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
+          umma_bf16_ts(tO, tP + kk * 8, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
         umma_commit(o_full);
         umma_commit(kv_empty(s));
       }
@@ -180,7 +195,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      if (j > 0) {  // P_{j-1} V_{j-1} has retired: O is stable and sP may be overwritten
+      if (j > 0) {  // P_{j-1} V_{j-1} has retired: O is stable and the P region of TMEM may be overwritten
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
@@ -225,9 +240,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             l += p[i];
           }
         }
-        store_tile_row32(sP, row, c * 32, p);
+        store_tmem_operand32(tP + lane_off + c * 16, p);
       }
-      fence_proxy_async_smem();
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);   // one arrival per warp: mbarrier operations serialise

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(EW_THREADS) layernorm_fwd_kernel(const XT* __r
 // gradient if given. dgamma/dbeta: per-lane register partials -> smem cross-warp reduce -> one red.add per column/CTA.
 // ------------------------------------------------------------------------------------------------------------------
 template <typename DT, typename XT, int NV>
-__global__ void __launch_bounds__(EW_THREADS) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
+__global__ void __launch_bounds__(EW_THREADS, (NV <= 4) ? 2 : 1) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
                                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ dx_resid,
                                                                    float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_out_bf16,

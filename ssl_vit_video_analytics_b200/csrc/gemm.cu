@@ -458,15 +458,20 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
   }
 }
 
-static int pick_block_n(int N, bool accumulate) {
-  const int cands[3] = {accumulate ? 192 : 256, 192, 128};  // accumulating GEMMs keep 32 TMEM columns for the row sums
-  for (int c : cands)
-    if (N % c == 0) return c;
-  // no exact fit: minimise padded columns, prefer the larger tile on ties
-  int best = 128, best_waste = 1 << 30;
+// Tile width: minimise (rounds over the SMs) x (time of one tile). A tile's time is ~ BLOCK_N plus a fixed part
+// (pipeline fill, epilogue tail); wide tiles re-read A less, narrow tiles quantise better when M is small.
+static int pick_block_n(int M, int N, int k_splits, bool accumulate) {
+  const int cands[3] = {256, 192, 128};
+  const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int sms = num_sms();
+  int best = 128;
+  long long best_cost = -1;
   for (int c : cands) {
-    const int waste = ((N + c - 1) / c) * c - N;
-    if (waste < best_waste) { best = c; best_waste = waste; }
+    if (accumulate && c > 192) continue;  // accumulating GEMMs keep 32 TMEM columns for the row sums
+    const long long units = m_tiles * ((N + c - 1) / c) * k_splits;
+    const long long rounds = (units + sms - 1) / sms;
+    const long long cost = rounds * (c + 48);
+    if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
   }
   return best;
 }
@@ -522,7 +527,6 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
     epi = out_dtype == VMAE_DTYPE_F32 ? EPI_F32 : EPI_BF16;
   }
 
-  const int block_n = pick_block_n(N, accumulate != 0);
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   if (k_splits > num_kb) k_splits = num_kb;
   {  // no empty splits
@@ -530,6 +534,7 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
     k_splits = (num_kb + per - 1) / per;
   }
 
+  const int block_n = pick_block_n(M, N, k_splits, accumulate != 0);
   GemmMaps maps;
   int rc;
   if (a_major == VMAE_MAJOR_K) {

@@ -55,17 +55,19 @@ __global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_kernel(const float*
     const int w0 = n % wp; n /= wp;
     const int h0 = n % hp;
     const int t0 = n / hp;
-    // gather pixels: source order (c, dt, py, px), px fastest
+    // gather pixels: source order (c, dt, py, px), px fastest; one 16-byte load covers 4 consecutive px (ps % 4 == 0)
     float s = 0.f;
-    for (int e = lane; e < D; e += 32) {
+    for (int e = lane * 4; e < D; e += 128) {
       const int px = e % ps;
       int r = e / ps;
       const int py = r % ps; r /= ps;
       const int dt = r % pt;
       const int c = r / pt;
-      const float v = __ldg(clip + ((((long long)b * 3 + c) * T + (t0 * pt + dt)) * H + (h0 * ps + py)) * W + (w0 * ps + px));
-      buf[((dt * ps + py) * ps + px) * 3 + c] = v;
-      s += v;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+          clip + ((((long long)b * 3 + c) * T + (t0 * pt + dt)) * H + (h0 * ps + py)) * W + (w0 * ps + px)));
+      float* dst = buf + ((dt * ps + py) * ps + px) * 3 + c;
+      dst[0] = v.x; dst[3] = v.y; dst[6] = v.z; dst[9] = v.w;
+      s += (v.x + v.y) + (v.z + v.w);
     }
     __syncwarp();
     float mean = 0.f, inv_std = 1.f;
@@ -366,6 +368,7 @@ extern "C" int vmae_masked_mse_fwd(const float* clip, const void* pred, int pred
                                    int B, int T, int H, int W, int pt, int ps, int norm_pix, void* stream) {
   VMAE_CHECK_ARG(clip && pred && mask && acc, "vmae_masked_mse_fwd: null pointer");
   VMAE_CHECK_ARG(B > 0 && pt > 0 && ps > 0 && T % pt == 0 && H % ps == 0 && W % ps == 0, "vmae_masked_mse_fwd: clip %dx%dx%d not divisible by tubelet %dx%dx%d", T, H, W, pt, ps, ps);
+  VMAE_CHECK_ARG(ps % 4 == 0 && W % 4 == 0 && ((uintptr_t)clip & 15) == 0, "vmae_masked_mse_fwd: patch size and width must be multiples of 4 and the clip 16-byte aligned");
   VMAE_CHECK_ARG(norm_pix >= 0 && norm_pix <= 2, "vmae_masked_mse_fwd: norm_pix must be 0, 1 or 2");
   const int D = pt * ps * ps * 3;
   VMAE_CHECK_ARG(D % 8 == 0, "vmae_masked_mse_fwd: token dim %d must be a multiple of 8", D);
