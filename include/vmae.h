@@ -121,6 +121,9 @@ int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* 
 /* ---- small memory-bound helpers -------------------------------------------------------------------------------- */
 int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+/* fp32 master weights -> bf16 operand copies for a whole parameter set in one launch. `table` is a DEVICE array of
+ * `count` entries {const float* src; bf16* dst; long long n;} (24 bytes each; src and dst 16-byte aligned). */
+int vmae_multi_cast_f32_to_bf16(const void* table, int count, void* stream);
 /* out = dy * gelu'(pre) (exact erf GELU, nn.GELU()); bf16, n elements (n % 8 == 0) */
 int vmae_gelu_bwd(const void* dy, const void* pre, void* out, long long n, void* stream);
 /* db[n] += sum_m dy[m,n]   (bias gradient; dy bf16 or fp32 [M, ld]) */

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(EW_THREADS) layernorm_fwd_kernel(const XT* __r
 // gradient if given. dgamma/dbeta: per-lane register partials -> smem cross-warp reduce -> one red.add per column/CTA.
 // ------------------------------------------------------------------------------------------------------------------
 template <typename DT, typename XT, int NV>
-__global__ void __launch_bounds__(EW_THREADS, (NV <= 4) ? 2 : 1) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
+__global__ void __launch_bounds__(EW_THREADS, (NV <= 3) ? 3 : ((NV <= 4) ? 2 : 1)) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
                                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ dx_resid,
                                                                    float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_out_bf16,
@@ -213,6 +213,29 @@ __global__ void __launch_bounds__(EW_THREADS) cast_f32_bf16_kernel(const float* 
   }
   for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
 }
+// one launch for a whole parameter set: entry t of the table = {src fp32, dst bf16, element count}
+struct CastEntry {
+  const float* src;
+  __nv_bfloat16* dst;
+  long long n;
+};
+__global__ void __launch_bounds__(EW_THREADS) multi_cast_f32_bf16_kernel(const CastEntry* __restrict__ table) {
+  const CastEntry e = table[blockIdx.y];
+  const long long n8 = e.n / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(e.src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.src) + 2 * i + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    reinterpret_cast<uint4*>(e.dst)[i] = u;
+  }
+  for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += stride) e.dst[i] = __float2bfloat16_rn(e.src[i]);
+}
+
 __global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
   const long long n4 = n / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -419,6 +442,14 @@ extern "C" int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void*
   if (n == 0) return VMAE_OK;
   VMAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "vmae_cast_f32_to_bf16: pointers must be 16-byte aligned");
   cast_f32_bf16_kernel<<<ew_grid(n / 8 + 1, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+extern "C" int vmae_multi_cast_f32_to_bf16(const void* table, int count, void* stream) {
+  VMAE_CHECK_ARG(count >= 0 && (count == 0 || table), "vmae_multi_cast_f32_to_bf16: bad args");
+  if (count == 0) return VMAE_OK;
+  VMAE_CHECK_ARG(count <= 65535, "vmae_multi_cast_f32_to_bf16: at most 65535 tensors per call");
+  multi_cast_f32_bf16_kernel<<<dim3(16, count), EW_THREADS, 0, (cudaStream_t)stream>>>((const CastEntry*)table);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }

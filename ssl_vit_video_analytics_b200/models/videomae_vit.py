@@ -128,6 +128,7 @@ class VideoMAEViT(nn.Module):
         x = x.contiguous()
         if vis_idx is None:
             vis_idx = self.visible_indices(mask)
+        ops.refresh_weight_cache(self)   # one launch: bf16 operand copies of every weight matrix
         n_vis = vis_idx.shape[1]
         Lv = Tp * n_vis
         patches, pos_rows = ops.TubeletGatherFn.apply(x, vis_idx, self.enc_temporal_pos_embed, self.enc_spatial_pos_embed, pt, ps)

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -176,6 +177,59 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+# id(parameter) -> (weakref to the parameter, bf16 operand copy made by WeightCache.refresh() for the current step)
+_WEIGHT_BF16 = {}
+
+
+def cast_weight(w: torch.Tensor) -> torch.Tensor:
+    """bf16 GEMM operand of a weight: the WeightCache copy if the owning model refreshed it this step, else a cast."""
+    e = _WEIGHT_BF16.get(id(w))
+    if e is not None and e[0]() is w and e[1].device == w.device:   # identity check: ids are recycled after a model dies
+        return e[1]
+    return cast_bf16(w)
+
+
+class WeightCache:
+    """bf16 copies of all matrix-shaped fp32 parameters of a module, refreshed with ONE kernel launch per step
+    (instead of one cast launch per weight). The model calls refresh() at the start of forward."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.ndim >= 2 and p.dtype == F32 and p.is_cuda and p.numel() >= 1024]
+        self.key = tuple((p.data_ptr(), p.numel()) for p in self.params)
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 7) // 8 * 8  # keep every copy 16-byte aligned
+        self.flat = torch.empty(total, device=dev, dtype=BF16)
+        self.copies = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        table = []
+        for p, c in zip(self.params, self.copies):
+            table += [p.data_ptr(), c.data_ptr(), p.numel()]
+        self.table = torch.tensor(table, dtype=torch.int64).to(dev)
+
+    def stale(self) -> bool:
+        return self.key != tuple((p.data_ptr(), p.numel()) for p in self.params)
+
+    def refresh(self) -> None:
+        L.check(_run("cast", 6.0 * self.flat.numel(), lambda: L.load().vmae_multi_cast_f32_to_bf16(
+            _p(self.table), len(self.params), _stream())), "vmae_multi_cast_f32_to_bf16")
+        _count()
+        for p, c in zip(self.params, self.copies):
+            _WEIGHT_BF16[id(p)] = (weakref.ref(p), c)
+
+
+def refresh_weight_cache(module: torch.nn.Module) -> None:
+    """Called by the models at the start of forward on CUDA: (re)build the cache if parameters moved, then one launch."""
+    cache = module.__dict__.get("_vmae_weight_cache")
+    if cache is None or cache.stale():
+        if not any(p.is_cuda for p in module.parameters()):
+            return
+        cache = WeightCache(module)
+        module.__dict__["_vmae_weight_cache"] = cache
+    cache.refresh()
+
+
 def cast_f32(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     if x.dtype == F32:
@@ -252,7 +306,7 @@ class LinearFn(torch.autograd.Function):
         _need_cuda(x, weight)
         shp = x.shape
         x2 = cast_bf16(x.reshape(-1, shp[-1]))
-        wb = cast_bf16(weight)
+        wb = cast_weight(weight)
         bf = bias.float().contiguous() if bias is not None else None
         pre = torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=BF16) if act == L.ACT_GELU else None
         y = linear_fwd(x2, wb, bf, act=act, aux_out=pre)
@@ -428,7 +482,7 @@ class TransformerBlockFn(torch.autograd.Function):
         f = lambda t: t.float().contiguous()
         ln1_w, ln1_b, ln2_w, ln2_b = f(ln1_w), f(ln1_b), f(ln2_w), f(ln2_b)
         qkv_b, proj_b, fc1_b, fc2_b = f(qkv_b), f(proj_b), f(fc1_b), f(fc2_b)
-        wq, wp, w1, w2 = cast_bf16(qkv_w), cast_bf16(proj_w), cast_bf16(fc1_w), cast_bf16(fc2_w)
+        wq, wp, w1, w2 = cast_weight(qkv_w), cast_weight(proj_w), cast_weight(fc1_w), cast_weight(fc2_w)
         ln1, mean1, rstd1 = layernorm_fwd(x, ln1_w, ln1_b)
         qkv = linear_fwd(ln1, wq, qkv_b)
         o, lse = attn_fwd(qkv, B, Lq, num_heads, hd)
@@ -489,7 +543,7 @@ class LinearResidualF32Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_bf16, weight, bias, residual):
-        wb = cast_bf16(weight.reshape(weight.shape[0], -1))
+        wb = cast_weight(weight).reshape(weight.shape[0], -1)
         y = linear_fwd(x_bf16, wb, bias.float().contiguous() if bias is not None else None, residual=residual.contiguous())
         ctx.save_for_backward(x_bf16, wb)
         ctx.w_shape = weight.shape
