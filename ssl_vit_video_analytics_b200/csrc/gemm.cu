@@ -241,6 +241,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================== UMMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // Descriptors are built ONCE; per UMMA only the 14-bit start-address field (bytes >> 4) advances. Building a
+      // descriptor from scratch costs ~15 dependent ALU ops per operand, which made this single issuing thread — not the
+      // tensor pipe — the limiter (4 UMMAs of 128 cycles each per K block need < 512 cycles of issue work).
+      // K-major: advance 16 elements (32 B) inside the 128 B swizzle row; SBO = 8 rows * 128 B.
+      // MN-major: advance 16 k-rows of 128 B; LBO = next 64-wide MN chunk (one TMA box), SBO = 8 k-rows.
+      const uint64_t dA0 = A_MN ? umma_smem_desc_sw128(smem_base, GEMM_BLOCK_K * 128, 1024) : umma_smem_desc_sw128(smem_base, 0, 1024);
+      const uint64_t dB0 = B_MN ? umma_smem_desc_sw128(smem_base + Cfg::A_BYTES, GEMM_BLOCK_K * 128, 1024)
+                                : umma_smem_desc_sw128(smem_base + Cfg::A_BYTES, 0, 1024);
+      const uint64_t dOnes = umma_smem_desc_sw128(ones_base, 0, 1024);
+      constexpr uint32_t A_STEP = (A_MN ? GEMM_UMMA_K * 128 : GEMM_UMMA_K * 2) >> 4;
+      constexpr uint32_t B_STEP = (B_MN ? GEMM_UMMA_K * 128 : GEMM_UMMA_K * 2) >> 4;
+      constexpr uint32_t STAGE_STEP = Cfg::STAGE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -251,25 +263,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const bool row_sums = (EPI == EPI_F32_ACCUM) && p.bias_grad != nullptr && n0 == 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t dA = dA0 + static_cast<uint64_t>(stage * STAGE_STEP);
+          const uint64_t dB = dB0 + static_cast<uint64_t>(stage * STAGE_STEP);
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row; SBO = 8 rows * 128 B.
-            // MN-major: advance 16 k-rows of 128 B; LBO = next 64-wide MN chunk (one TMA box), SBO = 8 k-rows.
-            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
-                                        : umma_smem_desc_sw128(sa + k * (GEMM_UMMA_K * 2), 0, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 128), GEMM_BLOCK_K * 128, 1024)
-                                        : umma_smem_desc_sw128(sb + k * (GEMM_UMMA_K * 2), 0, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (EPI == EPI_F32_ACCUM && p.bias_grad != nullptr && n0 == 0) {
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, dA + k * A_STEP, dB + k * B_STEP, idesc, acc);
+            if (row_sums) {
               // row sums of A over the contraction dimension = bias gradient: D2[128 x 16] += A * ones
               constexpr uint32_t idesc_ones = umma_idesc_bf16(GEMM_BLOCK_M, 16, A_MN, 0);
-              umma_bf16(tmem_base + 2 * BLOCK_N + as * 16, adesc, umma_smem_desc_sw128(ones_base + k * (GEMM_UMMA_K * 2), 0, 1024),
-                        idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + 2 * BLOCK_N + as * 16, dA + k * A_STEP, dOnes + k * ((GEMM_UMMA_K * 2) >> 4), idesc_ones, acc);
             }
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these UMMAs retire

@@ -2,9 +2,11 @@
 unchanged; file:line citations refer to that file).
 
 Transformer parts (Attention :86-106, Mlp :74-84, TinyViTBlock :108-130) run on the hand-written sm_100a kernels
-(tcgen05 GEMMs with fused epilogues, tcgen05 flash attention, warp-shuffle LayerNorm) through `ops`. The convolutional
-stages (Conv2d_BN :12-18, SELayer :20-34, MBConv :36-56, PatchEmbed :62-72) keep the reference arithmetic and key layout;
-their kernels are the K7 row of SURVEY.md §2b and are still dispatched by PyTorch in this round.
+(tcgen05 GEMMs with fused epilogues, tcgen05 flash attention, warp-shuffle LayerNorm) through `ops`. In the convolutional
+stages (Conv2d_BN :12-18, SELayer :20-34, MBConv :36-56, PatchEmbed :62-72) the point-wise (1x1) convolutions and the
+squeeze-excite Linears run on the same GEMM over the channels-last view of the feature map; the 3x3 stem / depthwise
+convolutions, BatchNorm statistics and elementwise activations keep the reference arithmetic and key layout and are
+still dispatched by PyTorch in this round (the rest of the K7 row of SURVEY.md §2b).
 """
 from __future__ import annotations
 
@@ -43,7 +45,10 @@ def _drop_path_active(m: nn.Module) -> bool:
 
 
 class Conv2d_BN(nn.Sequential):
-    """conv (no bias) followed by BatchNorm2d; children are named 'c' and 'bn' (tiny_vit.py:12-18)."""
+    """conv (no bias) followed by BatchNorm2d; children are named 'c' and 'bn' (tiny_vit.py:12-18).
+    Point-wise (1x1, ungrouped) convolutions — 70 % of the encoder's convolution FLOPs — run on the tcgen05 GEMM over the
+    channels-last view of the feature map (rows = pixels); 3x3 / depthwise convolutions and the BatchNorm statistics are
+    still PyTorch ops in this round."""
 
     def __init__(self, a, b, ks=1, stride=1, pad=0, dilation=1, groups=1, bn_weight_init=1):
         super().__init__()
@@ -51,6 +56,20 @@ class Conv2d_BN(nn.Sequential):
         self.add_module("bn", nn.BatchNorm2d(b))
         nn.init.constant_(self.bn.weight, bn_weight_init)
         nn.init.constant_(self.bn.bias, 0)
+
+    def _pointwise(self):
+        c = self.c
+        return c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and c.padding == (0, 0) and c.in_channels % 8 == 0 \
+            and c.out_channels % 8 == 0
+
+    def forward(self, x):
+        if x.is_cuda and self._pointwise():
+            n, cin, h, w = x.shape
+            rows = x.permute(0, 2, 3, 1).reshape(n * h * w, cin)          # free when x is channels_last
+            y = ops.linear(rows, self.c.weight, None)                        # [pixels, Cout]
+            y = y.view(n, h, w, -1).permute(0, 3, 1, 2)                      # NCHW view of channels-last data
+            return self.bn(y)
+        return self.bn(self.c(x))
 
 
 class SELayer(nn.Module):
@@ -68,8 +87,14 @@ class SELayer(nn.Module):
 
     def forward(self, x):
         n, c = x.shape[0], x.shape[1]
-        gate = self.fc(self.avg_pool(x).view(n, c)).view(n, c, 1, 1)
-        return x * gate.expand_as(x)
+        pooled = self.avg_pool(x).view(n, c)
+        if x.is_cuda and c % 32 == 0:
+            # the two bias-free Linears run on the tcgen05 GEMM; ReLU / sigmoid are elementwise glue on [n, c/4] and [n, c]
+            h = torch.relu(ops.linear(pooled, self.fc[0].weight, None))
+            gate = torch.sigmoid(ops.linear(h, self.fc[2].weight, None)).to(x.dtype)
+        else:
+            gate = self.fc(pooled)
+        return x * gate.view(n, c, 1, 1).expand_as(x)
 
 
 class MBConv(nn.Module):

@@ -299,22 +299,25 @@ def _amp_dtype_out(like_fp32: bool = False):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b): nn.Linear (+ optional GELU) on the tcgen05 GEMM. x: [..., K] bf16/fp32; y bf16."""
+    """y = act(x W^T + b): nn.Linear (+ optional GELU) on the tcgen05 GEMM. x: [..., K] bf16/fp32; y bf16.
+    `weight` may carry trailing singleton/kernel dims (e.g. a 1x1 Conv2d weight [N, K, 1, 1]); it is used as [N, -1]."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         _need_cuda(x, weight)
         shp = x.shape
         x2 = cast_bf16(x.reshape(-1, shp[-1]))
-        wb = cast_weight(weight)
+        n_out = weight.shape[0]
+        wb = cast_weight(weight).reshape(n_out, -1)
         bf = bias.float().contiguous() if bias is not None else None
-        pre = torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=BF16) if act == L.ACT_GELU else None
+        pre = torch.empty((x2.shape[0], n_out), device=x.device, dtype=BF16) if act == L.ACT_GELU else None
         y = linear_fwd(x2, wb, bf, act=act, aux_out=pre)
         ctx.save_for_backward(x2, wb, pre)
         ctx.has_bias = bias is not None
         ctx.in_shape = shp
         ctx.in_dtype = x.dtype
-        return y.reshape(*shp[:-1], weight.shape[0])
+        ctx.w_shape = weight.shape
+        return y.reshape(*shp[:-1], n_out)
 
     @staticmethod
     def backward(ctx, dy):
@@ -323,8 +326,15 @@ class LinearFn(torch.autograd.Function):
         if pre is not None:
             dy2 = gelu_bwd(dy2, pre)
         dx = linear_dgrad(dy2, wb) if ctx.needs_input_grad[0] else None
-        dw = linear_wgrad(dy2, x2) if ctx.needs_input_grad[1] else None
-        db = colsum(dy2) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw = db = None
+        if ctx.needs_input_grad[1] and ctx.has_bias and ctx.needs_input_grad[2]:
+            dw, db = linear_wgrad_bias(dy2, x2)
+        elif ctx.needs_input_grad[1]:
+            dw = linear_wgrad(dy2, x2)
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        if dw is not None:
+            dw = dw.reshape(ctx.w_shape)
         if dx is not None:
             dx = dx.reshape(ctx.in_shape)
             if ctx.in_dtype == F32:

@@ -1,4 +1,5 @@
-"""Launch a handful of representative kernels once each (for ncu). usage: prof_kernels.py [gemm|attn|all]"""
+"""Launch each hot kernel once at decoder-sized shapes (for `ncu --set full`): python tools/prof_kernels.py
+Round structure: the sequence below runs twice; profile the second round (skip = launches of one round)."""
 import sys
 from pathlib import Path
 
@@ -8,29 +9,33 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ssl_vit_video_analytics_b200 import _lib as L, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-what = sys.argv[1] if len(sys.argv) > 1 else "all"
 g = torch.Generator(device="cuda").manual_seed(0)
-M = 100352
-if what in ("gemm", "all"):
-    x = torch.randn(M, 384, device=dev, generator=g).bfloat16()
-    w1 = (torch.randn(1536, 384, device=dev, generator=g) * 0.05).bfloat16()
-    wp = (torch.randn(384, 384, device=dev, generator=g) * 0.05).bfloat16()
-    b1 = torch.randn(1536, device=dev, generator=g)
-    bp = torch.randn(384, device=dev, generator=g)
-    res = torch.randn(M, 384, device=dev, generator=g)
-    pre = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
-    for _ in range(2):
-        ops.gemm(x, w1, M, 1536, 384)                                              # plain, N=1536
-        ops.gemm(x, w1, M, 1536, 384, bias=b1, act=L.ACT_GELU, aux_out=pre)        # fc1
-        ops.gemm(x, wp, M, 384, 384, bias=bp, residual=res, out_dtype=torch.float32)  # proj + residual
-        ops.linear_dgrad(x, w1.t().contiguous(), aux_in=pre)                       # fc2 dgrad * gelu'
-        ops.linear_wgrad(pre, x)                                                   # wgrad 1536x384
-if what in ("attn", "all"):
-    B, Lq, H, hd = 64, 1568, 6, 64
-    qkv = torch.randn(B, Lq, 3 * H * hd, device=dev, generator=g).bfloat16()
-    dout = torch.randn(B * Lq, H * hd, device=dev, generator=g).bfloat16()
-    for _ in range(2):
-        out, lse = ops.attn_fwd(qkv, B, Lq, H, hd)
-        ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)
+M, D = 100352, 384
+x = torch.randn(M, D, device=dev, generator=g).bfloat16()
+xf = torch.randn(M, D, device=dev, generator=g)
+w1 = (torch.randn(1536, D, device=dev, generator=g) * 0.05).bfloat16()
+wp = (torch.randn(D, D, device=dev, generator=g) * 0.05).bfloat16()
+b1 = torch.randn(1536, device=dev, generator=g)
+bp = torch.randn(D, device=dev, generator=g)
+pre = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
+gm, bt = torch.randn(D, device=dev, generator=g), torch.randn(D, device=dev, generator=g)
+B, Lq, H, hd = 64, 1568, 6, 64
+qkv = torch.randn(B, Lq, 3 * H * hd, device=dev, generator=g).bfloat16()
+dout = torch.randn(B * Lq, H * hd, device=dev, generator=g).bfloat16()
+clip = torch.randn(16, 3, 16, 224, 224, device=dev, generator=g)
+pred = torch.randn(16, 1568, 1536, device=dev, generator=g).bfloat16()
+mask = (torch.rand(16, 1568, device=dev, generator=g) < 0.9)
+for _ in range(2):
+    ops.gemm(x, w1, M, 1536, D, bias=b1)                                            # 1 qkv/pred-like: bias, bf16 out
+    act = ops.gemm(x, w1, M, 1536, D, bias=b1, act=L.ACT_GELU, aux_out=pre)        # 2 fc1: bias + GELU + pre-activation
+    ops.gemm(x, wp, M, D, D, bias=bp, residual=xf, out_dtype=torch.float32)       # 3 proj: bias + fp32 residual
+    ops.linear_dgrad(x, w1.t().contiguous(), aux_in=pre)                           # 4 fc2 dgrad * gelu'
+    ops.linear_dgrad(pre, w1)                                                      # 5 fc1 dgrad (K = 1536)
+    ops.linear_wgrad_bias(pre, x)                                                  # 6 wgrad + bias grad
+    y, mean, rstd = ops.layernorm_fwd(xf, gm, bt)                                  # 7 LN fwd
+    ops.layernorm_bwd(x, xf, gm, mean, rstd, dx_resid=xf, want_bf16=True)          # 8 LN bwd
+    out, lse = ops.attn_fwd(qkv, B, Lq, H, hd)                                     # 9 attention fwd
+    ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)                                # 10-12 delta, dQ, dK/dV
+    ops.masked_mse(pred, clip, mask, 2, 16, 1)                                     # 13-14 loss (+ finalize)
 torch.cuda.synchronize()
 print("done")
