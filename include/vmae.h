@@ -42,8 +42,9 @@ int vmae_device_sm_count(void);
 
 /* ---- K1: GEMM on tcgen05/TMEM, TMA-fed, fused epilogue ---------------------------------------------------------
  * out[M,N] = epi( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulation.
- *   epi(v) = ( act(v + bias[n]) * gelu'(aux_in[m,n]) ) + residual[m,n]     (each term optional)
- *   aux_out (optional, with act=GELU) receives the pre-activation v + bias as bf16 (saved for backward).
+ *   epi(v) = ( act(v + bias[n]) * aux_in[m,n] ) + residual[m,n]            (each term optional)
+ *   aux_out (with act=GELU) receives gelu'(v + bias) as bf16 — the factor backward needs; the dgrad of the next
+ *   layer passes it back as aux_in, so its epilogue is a plain multiply.
  *   accumulate=1 (fp32 out): out += epi(...) with red.add — used for split-K weight gradients into .grad.
  * Replaces nn.Linear fwd/bwd: tiny_vit.py:79-81,93-94,105 ; mae_vit_adapter.py:24,40-53 ; tinyvit_mae.py:15,26.
  * forward  : A = x (MAJOR_K),  B = W [N,K] (MAJOR_K)
@@ -124,8 +125,8 @@ int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
 /* fp32 master weights -> bf16 operand copies for a whole parameter set in one launch. `table` is a DEVICE array of
  * `count` entries {const float* src; bf16* dst; long long n;} (24 bytes each; src and dst 16-byte aligned). */
 int vmae_multi_cast_f32_to_bf16(const void* table, int count, void* stream);
-/* out = dy * gelu'(pre) (exact erf GELU, nn.GELU()); bf16, n elements (n % 8 == 0) */
-int vmae_gelu_bwd(const void* dy, const void* pre, void* out, long long n, void* stream);
+/* out = dy * dact (dact = the gelu' tensor saved by the GELU epilogue); bf16, n elements (n % 4 == 0) */
+int vmae_gelu_bwd(const void* dy, const void* dact, void* out, long long n, void* stream);
 /* db[n] += sum_m dy[m,n]   (bias gradient; dy bf16 or fp32 [M, ld]) */
 int vmae_colsum_accum(const void* dy, int dy_dtype, long long ld, float* db, long long M, int N, void* stream);
 /* K8: z' = z + sigma * N(0,1) (privacy/feature_noise.py:4-7). Philox4x32-10 keyed by (seed, offset + element/4).

@@ -35,8 +35,8 @@ constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 enum : int {
   EPI_BF16 = 0,        // out bf16 = acc (+bias)
-  EPI_BF16_GELU = 1,   // out bf16 = gelu(acc + bias), aux_out bf16 = acc + bias
-  EPI_BF16_DGELU = 2,  // out bf16 = acc * gelu'(aux_in)
+  EPI_BF16_GELU = 1,   // out bf16 = gelu(acc + bias), aux_out bf16 = gelu'(acc + bias)   (saved for backward)
+  EPI_BF16_DGELU = 2,  // out bf16 = acc * aux_in                       (aux_in = the saved gelu')
   EPI_F32 = 3,         // out f32  = acc (+bias)
   EPI_F32_RESID = 4,   // out f32  = acc (+bias) + residual
   EPI_F32_ACCUM = 5,   // out f32 += acc            (TMA reduce-add; split-K)
@@ -357,12 +357,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (ET::HAS_IN) mbar_wait(in_bar(ew, b), (item >> 1) & 1u);
         if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
           if (EPI == EPI_BF16_GELU) {
+            // one evaluation of Phi(x) serves both gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x); the derivative is
+            // what backward needs, so it is stored instead of the pre-activation (same bytes, and the dgrad epilogue
+            // becomes a plain multiply)
+            float d[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = v[j];
+              const float cdf = normal_cdf(x);
+              const float pdf = 0.39894228040143268f * ex2_approx_f(-0.72134752044448170f * x * x);
+              d[j] = fmaf(x, pdf, cdf);
+              v[j] = x * cdf;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              sts_u4(box_bf16_slot(buf + ET::BOX_BYTES, r, j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-                     pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              sts_u4(box_bf16_slot(buf + ET::BOX_BYTES, r, j), pack2(d[8 * j], d[8 * j + 1]), pack2(d[8 * j + 2], d[8 * j + 3]),
+                     pack2(d[8 * j + 4], d[8 * j + 5]), pack2(d[8 * j + 6], d[8 * j + 7]));
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -374,10 +384,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t a = box_bf16_slot(buf, r, j);
             const uint4 h = lds_u4(a);
             const float2 h0 = unpack2(h.x), h1 = unpack2(h.y), h2 = unpack2(h.z), h3 = unpack2(h.w);
-            sts_u4(a, pack2(v[8 * j] * gelu_erf_grad(h0.x), v[8 * j + 1] * gelu_erf_grad(h0.y)),
-                   pack2(v[8 * j + 2] * gelu_erf_grad(h1.x), v[8 * j + 3] * gelu_erf_grad(h1.y)),
-                   pack2(v[8 * j + 4] * gelu_erf_grad(h2.x), v[8 * j + 5] * gelu_erf_grad(h2.y)),
-                   pack2(v[8 * j + 6] * gelu_erf_grad(h3.x), v[8 * j + 7] * gelu_erf_grad(h3.y)));
+            sts_u4(a, pack2(v[8 * j] * h0.x, v[8 * j + 1] * h0.y), pack2(v[8 * j + 2] * h1.x, v[8 * j + 3] * h1.y),
+                   pack2(v[8 * j + 4] * h2.x, v[8 * j + 5] * h2.y), pack2(v[8 * j + 6] * h3.x, v[8 * j + 7] * h3.y));
           }
         } else if (EPI == EPI_F32_RESID) {
 #pragma unroll

@@ -343,7 +343,7 @@ class LinearFn(torch.autograd.Function):
 
 
 def gelu_bwd(dy_bf16, pre_bf16):
-    """dy * gelu'(pre) (exact erf GELU), bf16 elementwise; used by the unfused LinearFn only."""
+    """dy * dact, where dact = gelu'(pre-activation) as saved by the GELU epilogue; used by the unfused LinearFn only."""
     out = torch.empty_like(dy_bf16)
     L.check(L.load().vmae_gelu_bwd(_p(dy_bf16), _p(pre_bf16), _p(out), dy_bf16.numel(), _stream()), "vmae_gelu_bwd")
     _count()
@@ -478,7 +478,7 @@ class TransformerBlockFn(torch.autograd.Function):
     It is the arithmetic of both TinyViTBlock (tiny_vit.py:108-130) and nn.TransformerEncoderLayer(norm_first=True,
     activation="gelu") (mae_vit_adapter.py:40-48) with dropout / drop-path inactive. Residual stream fp32 (as the
     reference's decoder under autocast), GEMM/attention operands bf16, fp32 accumulation.
-    Fusions: bias / bias+GELU(+pre-activation save) / bias+residual in GEMM epilogues, gelu' in the fc2-dgrad epilogue,
+    Fusions: bias / bias+GELU(+gelu' saved for backward) / bias+residual in GEMM epilogues, gelu' multiply in the fc2-dgrad epilogue,
     residual-gradient add + bf16 copy in the LayerNorm backward.
     """
 
@@ -519,7 +519,7 @@ class TransformerBlockFn(torch.autograd.Function):
         tgt = [(_direct_grad(p) if ctx.needs_input_grad[i + 1] else None) for i, p in enumerate(P)]
         (t_g1, t_b1, t_wq, t_bq, t_wp, t_bp, t_g2, t_b2, t_w1, t_bb1, t_w2, t_bb2) = tgt
         # ---- MLP branch
-        dh = linear_dgrad(dx2_b, w2, aux_in=h_pre)          # d(fc1 out) = (dx2 W2) * gelu'(h_pre)
+        dh = linear_dgrad(dx2_b, w2, aux_in=h_pre)          # d(fc1 out) = (dx2 W2) * gelu'(fc1 out); h_pre holds gelu'
         dw2, db2 = linear_wgrad_bias(dx2_b, act, t_w2, t_bb2)
         dln2 = linear_dgrad(dh, w1)
         dw1, db1 = linear_wgrad_bias(dh, ln2, t_w1, t_bb1)
