@@ -119,6 +119,38 @@ int vmae_decoder_input_bwd(const float* dx_dec, const int* vis_idx, const unsign
 int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* dspos, int B, int Tp, int n_vis, int D,
                       void* stream);
 
+/* ---- K7: TinyViT convolution kit on channels-last bf16 feature maps (rows = pixels), tiny_vit.py:12-72 ---------------
+ * Train-mode BatchNorm2d (batch statistics over the M = N*H*W rows, biased variance for normalisation, running statistics
+ * updated with `momentum` and the unbiased variance, as nn.BatchNorm2d) with optional fused exact GELU and residual add:
+ *   y = act((x - mean) * rstd * gamma + beta) (+ residual).  x, y, residual: bf16 [M, C]; mean/rstd: fp32 [C] (saved);
+ *   workspace: fp32 [2*C]; running_mean/var may be NULL.  act: VMAE_ACT_NONE | VMAE_ACT_GELU. */
+int vmae_bn_train_fwd(const void* x, const float* gamma, const float* beta, const void* residual, void* y, float* mean,
+                      float* rstd, float* running_mean, float* running_var, float* workspace, long long M, int C,
+                      float eps, float momentum, int act, void* stream);
+/* eval-mode / recompute form: statistics supplied (mean, rstd = 1/sqrt(var + eps)) */
+int vmae_bn_apply(const void* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                  const void* residual, void* y, long long M, int C, int act, void* stream);
+/* backward of the train-mode form: dx bf16 [M, C]; dgamma/dbeta fp32 [C] are ACCUMULATED; workspace fp32 [2*C]. */
+int vmae_bn_train_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, float* workspace, long long M, int C,
+                      int act, void* stream);
+
+/* depthwise 3x3 convolution, pad 1, stride 1|2, NHWC bf16 (tiny_vit.py:46): x [N,H,W,C] -> y [N,Ho,Wo,C];
+ * w: fp32 [C, 9] (nn.Conv2d weight [C,1,3,3] as stored). bwd: dx (bf16, may be NULL) and dw (fp32 [C,9], ACCUMULATED, may be NULL). */
+int vmae_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int H, int W, int C, int stride, void* stream);
+int vmae_dwconv3x3_bwd(const void* x, const void* dy, const float* w, void* dx, float* dw, int N, int H, int W, int C,
+                       int stride, void* stream);
+/* squeeze-excite (tiny_vit.py:20-34). pool: out[n,c] = scale * sum_p x[n,p,c] (dy == NULL) or scale * sum_p x*dy (gate gradient);
+ * scale: y[n,p,c] = a[n,p,c] * gate[n,c] (+ add_scale * add[n,c]); a == NULL broadcasts add_scale * add only.
+ * x/a/y/dy bf16 [N,HW,C]; gate/add/out fp32 [N,C]. */
+int vmae_se_pool(const void* x, const void* dy, float* out, int N, int HW, int C, float scale, void* stream);
+int vmae_se_scale(const void* a, const float* gate, const float* add, void* y, int N, int HW, int C, float add_scale, void* stream);
+/* im2col / col2im of 3x3 (pad 1) windows for the stem convolutions (tiny_vit.py:66-70); the GEMM is vmae_gemm_bf16.
+ * NHWC bf16 -> cols [N*Ho*Wo, 9*C] in (kh,kw,c) order; nchw_f32: fp32 NCHW image -> cols [N*Ho*Wo, KP] in (c,kh,kw) order, zero padded. */
+int vmae_im2col3x3(const void* x, void* col, int N, int H, int W, int C, int stride, void* stream);
+int vmae_col2im3x3(const void* dcol, void* dx, int N, int H, int W, int C, int stride, void* stream);
+int vmae_im2col3x3_nchw_f32(const float* x, void* col, int N, int Cin, int H, int W, int stride, int KP, void* stream);
+
 /* ---- small memory-bound helpers -------------------------------------------------------------------------------- */
 int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);

@@ -36,6 +36,16 @@ SIGNATURES = {
     "vmae_decoder_input_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vmae_decoder_input_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vmae_pos_rows_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "vmae_bn_train_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _f, _f, _i, _p],
+    "vmae_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _p],
+    "vmae_bn_train_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _p],
+    "vmae_dwconv3x3_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_dwconv3x3_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_se_pool": [_p, _p, _p, _i, _i, _i, _f, _p],
+    "vmae_se_scale": [_p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "vmae_im2col3x3": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_col2im3x3": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_im2col3x3_nchw_f32": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "vmae_cast_f32_to_bf16": [_p, _p, _ll, _p],
     "vmae_cast_bf16_to_f32": [_p, _p, _ll, _p],
     "vmae_multi_cast_f32_to_bf16": [_p, _i, _p],

@@ -44,11 +44,20 @@ def _drop_path_active(m: nn.Module) -> bool:
     return isinstance(m, DropPath) and m.drop_prob > 0.0 and m.training
 
 
+def _nchw_view(rows_nhwc):
+    """[N, H, W, C] contiguous -> NCHW view of the same (channels-last) memory."""
+    return rows_nhwc.permute(0, 3, 1, 2)
+
+
 class Conv2d_BN(nn.Sequential):
     """conv (no bias) followed by BatchNorm2d; children are named 'c' and 'bn' (tiny_vit.py:12-18).
-    Point-wise (1x1, ungrouped) convolutions — 70 % of the encoder's convolution FLOPs — run on the tcgen05 GEMM over the
-    channels-last view of the feature map (rows = pixels); 3x3 / depthwise convolutions and the BatchNorm statistics are
-    still PyTorch ops in this round."""
+
+    On CUDA the feature map lives channels-last in bf16 and every piece runs on the sm_100a kernels:
+      * 1x1 convolution            -> tcgen05 GEMM over rows = pixels,
+      * dense 3x3 (pad 1, stem)    -> im2col kernel + the same GEMM (the 3-channel image is gathered from fp32 NCHW),
+      * depthwise 3x3 (pad 1)      -> depthwise kernel,
+      * train-mode BatchNorm       -> statistics + apply kernels, with the following GELU and the MBConv residual fused.
+    `forward(x, act=False, residual=None)`: act/residual are the fusion hooks used by MBConv / PatchEmbed."""
 
     def __init__(self, a, b, ks=1, stride=1, pad=0, dilation=1, groups=1, bn_weight_init=1):
         super().__init__()
@@ -57,19 +66,56 @@ class Conv2d_BN(nn.Sequential):
         nn.init.constant_(self.bn.weight, bn_weight_init)
         nn.init.constant_(self.bn.bias, 0)
 
-    def _pointwise(self):
+    def _kind(self):
         c = self.c
-        return c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and c.padding == (0, 0) and c.in_channels % 8 == 0 \
-            and c.out_channels % 8 == 0
+        if c.dilation != (1, 1) or c.out_channels % 8 != 0:
+            return None
+        if c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0) and c.groups == 1 and c.in_channels % 8 == 0:
+            return "pointwise"
+        if c.kernel_size == (3, 3) and c.padding == (1, 1) and c.stride in ((1, 1), (2, 2)):
+            if c.groups == c.in_channels == c.out_channels:
+                return "depthwise"
+            if c.groups == 1:
+                return "dense3x3" if c.in_channels % 8 == 0 else "image3x3"
+        return None
 
-    def forward(self, x):
-        if x.is_cuda and self._pointwise():
-            n, cin, h, w = x.shape
-            rows = x.permute(0, 2, 3, 1).reshape(n * h * w, cin)          # free when x is channels_last
-            y = ops.linear(rows, self.c.weight, None)                        # [pixels, Cout]
-            y = y.view(n, h, w, -1).permute(0, 3, 1, 2)                      # NCHW view of channels-last data
-            return self.bn(y)
-        return self.bn(self.c(x))
+    def _conv_rows(self, x, kind):
+        """-> (rows bf16 [M, Cout], (N, Ho, Wo))"""
+        c = self.c
+        st = c.stride[0]
+        if kind == "image3x3":
+            kp = (c.in_channels * 9 + 7) // 8 * 8
+            col, ho, wo = ops.im2col3x3_image(x, st, kp)
+            w2d = torch.nn.functional.pad(c.weight.reshape(c.out_channels, -1), (0, kp - c.in_channels * 9))
+            return ops.LinearFn.apply(col, w2d, None, L.ACT_NONE), (x.shape[0], ho, wo)
+        xr = ops.as_nhwc_bf16(x)
+        n, h, w, cin = xr.shape
+        if kind == "pointwise":
+            return ops.LinearFn.apply(xr.view(n * h * w, cin), c.weight, None, L.ACT_NONE), (n, h, w)
+        if kind == "depthwise":
+            y = ops.DepthwiseConv3x3Fn.apply(xr, c.weight, st)
+            return y.view(-1, cin), (n, y.shape[1], y.shape[2])
+        col = ops.Im2col3x3Fn.apply(xr, st)                                   # dense3x3, (kh, kw, c) column order
+        w2d = c.weight.permute(0, 2, 3, 1).reshape(c.out_channels, -1)
+        ho, wo = (h - 1) // st + 1, (w - 1) // st + 1
+        return ops.LinearFn.apply(col, w2d, None, L.ACT_NONE), (n, ho, wo)
+
+    def forward(self, x, act=False, residual=None):
+        kind = self._kind() if x.is_cuda else None
+        bn = self.bn
+        if kind is None or not bn.training or bn.momentum is None or not bn.track_running_stats:
+            # eval-mode statistics / exotic configurations keep the reference ops
+            y = bn(self.c(x))
+            if act:
+                y = torch.nn.functional.gelu(y)
+            return y if residual is None else y + residual
+        rows, (n, ho, wo) = self._conv_rows(x, kind)
+        res_rows = ops.as_nhwc_bf16(residual).view(rows.shape) if residual is not None else None
+        y = ops.BatchNormActFn.apply(rows, bn.weight, bn.bias, bn.running_mean, bn.running_var, res_rows, bn.eps, bn.momentum,
+                                     L.ACT_GELU if act else L.ACT_NONE)
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        return _nchw_view(y.view(n, ho, wo, -1))
 
 
 class SELayer(nn.Module):
@@ -87,19 +133,26 @@ class SELayer(nn.Module):
 
     def forward(self, x):
         n, c = x.shape[0], x.shape[1]
-        pooled = self.avg_pool(x).view(n, c)
         if x.is_cuda and c % 32 == 0:
-            # the two bias-free Linears run on the tcgen05 GEMM; ReLU / sigmoid are elementwise glue on [n, c/4] and [n, c]
-            h = torch.relu(ops.linear(pooled, self.fc[0].weight, None))
-            gate = torch.sigmoid(ops.linear(h, self.fc[2].weight, None)).to(x.dtype)
-        else:
-            gate = self.fc(pooled)
+            # pool / gating kernels on the channels-last rows; the two bias-free Linears on the tcgen05 GEMM; ReLU and
+            # sigmoid are elementwise glue on the tiny [n, c/4] and [n, c] tensors
+            xr = ops.as_nhwc_bf16(x)
+            h_, w_ = xr.shape[1], xr.shape[2]
+            rows = xr.view(n, h_ * w_, c)
+            pooled = ops.SEPoolFn.apply(rows)
+            hid = torch.relu(ops.cast_f32_autograd(ops.LinearFn.apply(pooled, self.fc[0].weight, None, L.ACT_NONE)))
+            gate = torch.sigmoid(ops.cast_f32_autograd(ops.LinearFn.apply(hid, self.fc[2].weight, None, L.ACT_NONE)))
+            y = _nchw_view(ops.SEScaleFn.apply(rows, gate).view(n, h_, w_, c))
+            if x.dtype != ops.BF16:   # eval-mode neighbours run the reference ops in the caller's dtype
+                y = ops.cast_f32_autograd(y.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2).to(x.dtype)
+            return y
+        gate = self.fc(self.avg_pool(x).view(n, c))
         return x * gate.view(n, c, 1, 1).expand_as(x)
 
 
 class MBConv(nn.Module):
     """expand 1x1 -> depthwise 3x3 -> SE -> project 1x1 (BN gamma initialised to 0); residual only when the shape is kept
-    (tiny_vit.py:36-56)."""
+    (tiny_vit.py:36-56). GELUs are fused into the preceding BatchNorm kernels, the residual into the last one."""
 
     def __init__(self, in_chans, out_chans, expand_ratio=4, stride=1, drop_path=0.0):
         super().__init__()
@@ -118,7 +171,22 @@ class MBConv(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        y = self.conv(x)
+        mods = list(self.conv)
+        y = x
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, Conv2d_BN):
+                fuse_act = i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU)
+                last = i == len(mods) - 1
+                fuse_res = last and self.use_res_connect and not _drop_path_active(self.drop_path)
+                y = m(y, act=fuse_act, residual=x if fuse_res else None)
+                if fuse_res:
+                    return y
+                i += 2 if fuse_act else 1
+            else:
+                y = m(y)
+                i += 1
         return x + self.drop_path(y) if self.use_res_connect else y
 
 
@@ -134,7 +202,8 @@ class PatchEmbed(nn.Module):
         )
 
     def forward(self, x):
-        return self.patch_embed(x)
+        y = self.patch_embed[0](x, act=True)      # GELU (index 1) fused into the BatchNorm kernel
+        return self.patch_embed[2](y)
 
 
 class Mlp(nn.Module):
@@ -239,19 +308,26 @@ class TinyViT(nn.Module):
             return checkpoint.checkpoint(stage, x, use_reentrant=False)
         return stage(x)
 
+    @staticmethod
+    def _boundary(x):
+        """Internally the CUDA path keeps bf16 channels-last maps; outside autocast callers get fp32 like the reference."""
+        if x.is_cuda and x.dtype == ops.BF16 and not torch.is_autocast_enabled("cuda"):
+            return ops.cast_f32_autograd(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+        return x
+
     def forward_stage3(self, x):
         """MAE pre-training interface: stem + stages 0..2 -> [BT, 384, S/8, S/8] (tiny_vit.py:166-176)."""
         x = self.patch_embed(x)
         for s in range(3):
             x = self._run_stage(self.stages[s], x)
-        return x
+        return self._boundary(x)
 
     def forward(self, x):
         """Classification / finetune interface: all four stages (tiny_vit.py:178-186)."""
         x = self.patch_embed(x)
         for stage in self.stages:
             x = self._run_stage(stage, x)
-        return x
+        return self._boundary(x)
 
 
 def tiny_vit_21m_variant(img_size=112, use_checkpoint=True, **kwargs):

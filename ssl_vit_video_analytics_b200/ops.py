@@ -716,3 +716,169 @@ def scale_f32(x, alpha, out=None, accumulate=False):
     L.check(L.load().vmae_scale_f32(_p(xc), _p(out), float(alpha), 1 if accumulate else 0, xc.numel(), _stream()), "vmae_scale_f32")
     _count()
     return out
+
+
+# ======================================================================================================================
+# K7 — TinyViT convolution kit (channels-last bf16 feature maps; tiny_vit.py:12-72)
+# ======================================================================================================================
+def as_nhwc_bf16(x):
+    """NCHW tensor (any memory format / dtype) -> contiguous bf16 [N, H, W, C]; free for a channels-last bf16 input."""
+    t = x.permute(0, 2, 3, 1)
+    if t.dtype != BF16:
+        t = cast_bf16_autograd(t.contiguous())
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class BatchNormActFn(torch.autograd.Function):
+    """Train-mode BatchNorm2d over rows [M, C] (+ optional exact GELU, + optional residual), bf16 in / bf16 out, fp32
+    statistics; updates running_mean / running_var in place like nn.BatchNorm2d (momentum, unbiased variance)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, act):
+        _need_cuda(x, gamma)
+        M, Cc = x.shape
+        g, b = gamma.float().contiguous(), beta.float().contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty((Cc,), device=x.device, dtype=F32)
+        rstd = torch.empty((Cc,), device=x.device, dtype=F32)
+        ws = torch.empty((2 * Cc,), device=x.device, dtype=F32)
+        nbytes = float(M) * Cc * 2 * (3 + (1 if residual is not None else 0))
+        L.check(_run("batchnorm_fwd", nbytes, lambda: L.load().vmae_bn_train_fwd(
+            _p(x), _p(g), _p(b), _p(residual), _p(y), _p(mean), _p(rstd), _p(running_mean), _p(running_var), _p(ws), M, Cc, float(eps),
+            float(momentum), int(act), _stream())), "vmae_bn_train_fwd")
+        _count(3)
+        ctx.save_for_backward(x, g, b, mean, rstd)
+        ctx.act = int(act)
+        ctx.has_res = residual is not None
+        ctx.mark_non_differentiable(mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, b, mean, rstd = ctx.saved_tensors
+        M, Cc = x.shape
+        dy = cast_bf16(dy.contiguous())
+        dx = torch.empty_like(x)
+        dg = torch.zeros((Cc,), device=x.device, dtype=F32)
+        db = torch.zeros((Cc,), device=x.device, dtype=F32)
+        ws = torch.empty((2 * Cc,), device=x.device, dtype=F32)
+        L.check(_run("batchnorm_bwd", float(M) * Cc * 2 * 5, lambda: L.load().vmae_bn_train_bwd(
+            _p(x), _p(dy), _p(g), _p(b), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), M, Cc, ctx.act, _stream())), "vmae_bn_train_bwd")
+        _count(2)
+        return dx, dg, db, None, None, (dy if ctx.has_res else None), None, None, None
+
+
+class DepthwiseConv3x3Fn(torch.autograd.Function):
+    """Depthwise 3x3, pad 1, stride 1|2 on NHWC bf16; weight = nn.Conv2d weight [C, 1, 3, 3] (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        _need_cuda(x, weight)
+        N, H, W, Cc = x.shape
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        w = weight.float().contiguous()
+        y = torch.empty((N, Ho, Wo, Cc), device=x.device, dtype=BF16)
+        L.check(_run("dwconv_fwd", float(x.numel() + y.numel()) * 2, lambda: L.load().vmae_dwconv3x3_fwd(
+            _p(x), _p(w), _p(y), N, H, W, Cc, stride, _stream())), "vmae_dwconv3x3_fwd")
+        _count()
+        ctx.save_for_backward(x, w)
+        ctx.stride = stride
+        ctx.w_shape = weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        N, H, W, Cc = x.shape
+        dy = cast_bf16(dy.contiguous())
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros((Cc, 9), device=x.device, dtype=F32) if ctx.needs_input_grad[1] else None
+        L.check(_run("dwconv_bwd", float(x.numel() * 2 + dy.numel() * 2) * 2, lambda: L.load().vmae_dwconv3x3_bwd(
+            _p(x), _p(dy), _p(w), _p(dx), _p(dw), N, H, W, Cc, ctx.stride, _stream())), "vmae_dwconv3x3_bwd")
+        _count(2)
+        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), None
+
+
+class SEPoolFn(torch.autograd.Function):
+    """Global average pool per image: bf16 [N, HW, C] -> fp32 [N, C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, HW, Cc = x.shape
+        out = torch.empty((N, Cc), device=x.device, dtype=F32)
+        L.check(L.load().vmae_se_pool(_p(x), None, _p(out), N, HW, Cc, 1.0 / HW, _stream()), "vmae_se_pool")
+        _count()
+        ctx.shape = (N, HW, Cc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        N, HW, Cc = ctx.shape
+        dx = torch.empty((N, HW, Cc), device=dpooled.device, dtype=BF16)
+        # dx[n,p,c] = dpooled[n,c] / HW  (broadcast form of the gating kernel)
+        L.check(L.load().vmae_se_scale(None, None, _p(dpooled.float().contiguous()), _p(dx), N, HW, Cc, 1.0 / HW, _stream()), "vmae_se_scale")
+        _count()
+        return dx
+
+
+class SEScaleFn(torch.autograd.Function):
+    """y[n,p,c] = x[n,p,c] * gate[n,c]; x bf16 [N,HW,C], gate fp32 [N,C]."""
+
+    @staticmethod
+    def forward(ctx, x, gate):
+        N, HW, Cc = x.shape
+        gate = gate.float().contiguous()
+        y = torch.empty_like(x)
+        L.check(_run("se_scale", float(x.numel()) * 4, lambda: L.load().vmae_se_scale(_p(x), _p(gate), None, _p(y), N, HW, Cc, 0.0, _stream())),
+                "vmae_se_scale")
+        _count()
+        ctx.save_for_backward(x, gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gate = ctx.saved_tensors
+        N, HW, Cc = x.shape
+        dy = cast_bf16(dy.contiguous())
+        dx = torch.empty_like(x)
+        dgate = torch.empty((N, Cc), device=x.device, dtype=F32)
+        lib = L.load()
+        L.check(lib.vmae_se_scale(_p(dy), _p(gate), None, _p(dx), N, HW, Cc, 0.0, _stream()), "vmae_se_scale")
+        L.check(lib.vmae_se_pool(_p(x), _p(dy), _p(dgate), N, HW, Cc, 1.0, _stream()), "vmae_se_pool")
+        _count(2)
+        return dx, dgate
+
+
+class Im2col3x3Fn(torch.autograd.Function):
+    """NHWC bf16 -> [N*Ho*Wo, 9*C] window matrix in (kh, kw, c) order (pad 1); backward is the col2im gather."""
+
+    @staticmethod
+    def forward(ctx, x, stride):
+        N, H, W, Cc = x.shape
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        col = torch.empty((N * Ho * Wo, 9 * Cc), device=x.device, dtype=BF16)
+        L.check(L.load().vmae_im2col3x3(_p(x), _p(col), N, H, W, Cc, stride, _stream()), "vmae_im2col3x3")
+        _count()
+        ctx.geom = (N, H, W, Cc, stride)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        N, H, W, Cc, stride = ctx.geom
+        dcol = cast_bf16(dcol.contiguous())
+        dx = torch.empty((N, H, W, Cc), device=dcol.device, dtype=BF16)
+        L.check(L.load().vmae_col2im3x3(_p(dcol), _p(dx), N, H, W, Cc, stride, _stream()), "vmae_col2im3x3")
+        _count()
+        return dx, None
+
+
+def im2col3x3_image(x_nchw_f32, stride, kp):
+    """fp32 NCHW image -> bf16 [N*Ho*Wo, kp] window matrix in (c, kh, kw) order, zero padded to kp columns (no gradient:
+    the input is data)."""
+    x = x_nchw_f32.detach().float().contiguous()
+    N, Cin, H, W = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    col = torch.empty((N * Ho * Wo, kp), device=x.device, dtype=BF16)
+    L.check(L.load().vmae_im2col3x3_nchw_f32(_p(x), _p(col), N, Cin, H, W, stride, kp, _stream()), "vmae_im2col3x3_nchw_f32")
+    _count()
+    return col, Ho, Wo

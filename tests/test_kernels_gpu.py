@@ -266,3 +266,90 @@ def test_fedavg_aggregate_on_device_is_bit_exact_with_cpu(env):
     new = fedavg_aggregate(glob, clients, w)
     for k in ref:
         assert torch.equal(new[k], ref[k]), k
+
+
+# ---- K7: TinyViT convolution kit ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,Cc,act,res", [(3000, 96, True, False), (5000, 384, True, True), (777, 48, False, False), (64, 768, False, True)])
+def test_batchnorm_train_fwd_bwd(env, M, Cc, act, res):
+    ops, L, dev, g = env
+    x = (torch.randn(M, Cc, device=dev, generator=g) * 1.7 + 0.3).bfloat16()
+    gm = torch.rand(Cc, device=dev, generator=g) + 0.5
+    bt = torch.randn(Cc, device=dev, generator=g) * 0.1
+    rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    r = torch.randn(M, Cc, device=dev, generator=g).bfloat16() if res else None
+    xg = x.clone().requires_grad_(True)
+    gg, bg = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    y = ops.BatchNormActFn.apply(xg, gg, bg, rm, rv, r, 1e-5, 0.1, L.ACT_GELU if act else L.ACT_NONE)
+    # reference: nn.functional.batch_norm in train mode on the NCHW view
+    xr = x.float().clone().requires_grad_(True)
+    gr, br = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    yr = F.batch_norm(xr.t().reshape(1, Cc, M, 1), rm2, rv2, gr, br, True, 0.1, 1e-5).reshape(Cc, M).t()
+    if act:
+        yr = F.gelu(yr)
+    if res:
+        yr = yr + r.float()
+    assert relerr(y, yr) < BF16_TOL
+    assert relerr(rm, rm2) < 1e-3 and relerr(rv, rv2) < 1e-3
+    dy = torch.randn(M, Cc, device=dev, generator=g).bfloat16()
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert relerr(xg.grad, xr.grad) < 2e-2
+    assert relerr(gg.grad, gr.grad) < 2e-2 and relerr(bg.grad, br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("N,H,W,Cc,stride", [(2, 14, 14, 384, 1), (3, 28, 28, 768, 2), (1, 7, 9, 96, 2), (2, 8, 8, 48, 1)])
+def test_depthwise_conv3x3_fwd_bwd(env, N, H, W, Cc, stride):
+    ops, L, dev, g = env
+    x = torch.randn(N, H, W, Cc, device=dev, generator=g).bfloat16().requires_grad_(True)
+    w = (torch.randn(Cc, 1, 3, 3, device=dev, generator=g) * 0.3).requires_grad_(True)
+    y = ops.DepthwiseConv3x3Fn.apply(x, w, stride)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, 1, 1, Cc)
+    assert y.shape == yr.permute(0, 2, 3, 1).shape
+    assert relerr(y, yr.permute(0, 2, 3, 1)) < BF16_TOL
+    dy = torch.randn_like(yr)
+    y.backward(dy.permute(0, 2, 3, 1).bfloat16())
+    yr.backward(dy.bfloat16().float())
+    assert relerr(x.grad, xr.grad.permute(0, 2, 3, 1)) < BF16_TOL
+    assert relerr(w.grad, wr.grad) < 2e-3
+
+
+def test_squeeze_excite_pool_and_scale(env):
+    ops, L, dev, g = env
+    N, HW, Cc = 3, 49, 384
+    x = torch.randn(N, HW, Cc, device=dev, generator=g).bfloat16().requires_grad_(True)
+    gate = torch.rand(N, Cc, device=dev, generator=g).requires_grad_(True)
+    pooled = ops.SEPoolFn.apply(x)
+    y = ops.SEScaleFn.apply(x, gate)
+    xr, gr = x.detach().float().requires_grad_(True), gate.detach().clone().requires_grad_(True)
+    pr, yr = xr.mean(1), xr * gr[:, None, :]
+    assert relerr(pooled, pr) < 1e-5 and relerr(y, yr) < BF16_TOL
+    dp, dy = torch.randn_like(pr), torch.randn_like(yr).bfloat16()
+    (pooled * dp).sum().backward(retain_graph=True)
+    y.backward(dy)
+    (pr * dp).sum().backward()
+    yr.backward(dy.float())
+    assert relerr(x.grad, xr.grad) < 2e-2 and relerr(gate.grad, gr.grad) < 1e-3
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_im2col_col2im_and_image_im2col(env, stride):
+    ops, L, dev, g = env
+    N, H, W, Cc = 2, 9, 10, 48
+    x = torch.randn(N, H, W, Cc, device=dev, generator=g).bfloat16().requires_grad_(True)
+    col = ops.Im2col3x3Fn.apply(x, stride)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    unf = F.unfold(xr, 3, padding=1, stride=stride)                    # [N, C*9, P] in (c, kh, kw) order
+    P = unf.shape[-1]
+    ref = unf.view(N, Cc, 9, P).permute(0, 3, 2, 1).reshape(N * P, 9 * Cc)   # -> (kh, kw, c)
+    assert torch.equal(col.float(), ref.bfloat16().float())
+    dcol = torch.randn_like(ref).bfloat16()
+    col.backward(dcol)
+    ref.backward(dcol.float())
+    assert relerr(x.grad, xr.grad.permute(0, 2, 3, 1)) < BF16_TOL
+    img = torch.randn(N, 3, H, W, device=dev, generator=g)
+    c2, ho, wo = ops.im2col3x3_image(img, stride, 32)
+    u2 = F.unfold(img, 3, padding=1, stride=stride).permute(0, 2, 1).reshape(-1, 27)
+    assert torch.equal(c2[:, :27].float(), u2.bfloat16().float()) and float(c2[:, 27:].abs().max()) == 0.0
