@@ -41,7 +41,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                                           str(self.index)], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -175,20 +175,52 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = PER_GPU_BATCH if args.batch is None else args.batch
     torch.manual_seed(0)
-    model = VideoMAEViT(cfg).to(dev).train()
-    ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
-    clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
+    if args.workload == "tinyvit":
+        # the drop-in TinyVideoMAE at the reference's own configs/ssl_mae.yaml shapes (reported next to the headline)
+        from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+        from ssl_vit_video_analytics_b200.models import TinyVideoMAE, tiny_vit_21m_variant
+        from ssl_vit_video_analytics_b200.train_ssl_mae import mae_step_loss
+
+        B = 40 if args.batch is None else args.batch
+        tcfg = {"dataset": {"clip_len": 16, "image_size": 112},
+                "model": {"decoder_embed_dim": 384, "decoder_depth": 4, "decoder_num_heads": 6, "decoder_dropout": 0.0}}
+        model = TinyVideoMAE(tiny_vit_21m_variant(img_size=112, use_checkpoint=False, drop_path_rate=0.0), tcfg)
+        # "perturbed init" (SURVEY.md §0 fact 6): at the reference's literal init every stride-2 MBConv ends in a BatchNorm
+        # with gamma = 0, the encoder output is identically zero and the arithmetic is mostly on zeros
+        gen = torch.Generator().manual_seed(1234)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if name.endswith(".bn.weight"):
+                    p.copy_(torch.rand(p.shape, generator=gen) + 0.5)
+                elif name.endswith("bias"):
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.02)
+        model = model.to(dev).train()
+        ddp = GradientBucketer(model, bucket_mb=32.0, exclude=("encoder.stages.3.",))
+        g = torch.Generator().manual_seed(rank)
+        clip_h = torch.randn(B, 3, 16, 112, 112, generator=g)
+        torch.manual_seed(42 + rank)
+        mask_d = get_tube_mask(B, 16, 196, 0.9).to(dev)
+
+        def loss_fn(clip):
+            return mae_step_loss(model, clip, mask_d, True)[0]
+    else:
+        B = PER_GPU_BATCH if args.batch is None else args.batch
+        model = VideoMAEViT(cfg).to(dev).train()
+        ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())
+        clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
+        mask_d, vis_d = mask_h.to(dev), vis_h.to(dev)
+
+        def loss_fn(clip):
+            return model.training_loss(clip, mask_d, vis_d)
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05, fused=True)
     clip_pinned = [clip_h.pin_memory(), clip_h.clone().pin_memory()]
-    mask_d, vis_d = mask_h.to(dev), vis_h.to(dev)
     clip_d = clip_h.to(dev)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def step(clip):
         ddp.zero_grad()
-        loss = model.training_loss(clip, mask_d, vis_d)
+        loss = loss_fn(clip)
         loss.backward()
         ddp.finish_gradient_sync()
         opt.step()
@@ -286,6 +318,10 @@ def run_ours(args, cfg):
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    if args.workload == "tinyvit":
+        workload, step_gflop = "drop-in TinyVideoMAE (TinyViT-21M encoder), 16x112x112, patch 8, mask 0.9 (configs/ssl_mae.yaml)", 740.3
+    else:
+        workload, step_gflop = WORKLOAD, STEP_GFLOP_PER_CLIP
     tensor_classes = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "attn_fwd", "attn_bwd"]
     dom = max((k for k in tensor_classes if k in prof), key=lambda k: prof[k]["ms"])
     d = prof[dom]
@@ -293,15 +329,15 @@ def run_ours(args, cfg):
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_per_step": d["launches"], "ms_per_step": d["ms"],
-                "step_frac_of_tensor_roofline": (B * STEP_GFLOP_PER_CLIP / 1e3) / (ms_step / 1e3) / peaks["bf16_tflops_sustained"],
+                "step_frac_of_tensor_roofline": (B * step_gflop / 1e3) / (ms_step / 1e3) / peaks["bf16_tflops_sustained"],
                 "by_kernel_class": {k: {"ms_per_step": round(v["ms"], 3), "launches_per_step": v["launches"],
                                         ("tflops" if k in tensor_classes else "gbs"): round(v["work"] / (v["ms"] / 1e3) / (1e12 if k in tensor_classes else 1e9), 1)}
                                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "l2_policy": "inputs larger than L2 (616 MB clip batch, >10 GB activations per step)", "optimizer": "AdamW(fused)",
+        "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "AdamW(fused)",
                    "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
@@ -309,7 +345,7 @@ def run_ours(args, cfg):
         "gpu_launches": launches,
         "roofline": roofline,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "vit_s":
         threads = os.cpu_count() or 1
         try:
             v, ms = time_cpu_reference(cfg, 2, 3, 1, threads)
@@ -325,11 +361,13 @@ def run_ours(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit"],
+                    help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from ssl_vit_video_analytics_b200.models.videomae_vit import DEFAULT_CONFIG

@@ -52,58 +52,60 @@ __device__ __forceinline__ float cv_gelu_grad(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// column reductions over rows [M, C] (C % 8 == 0). grid = (ceil(C/256), slabs); lane owns 8 channels.
-// MODE 0: acc[0][c] += sum x,  acc[1][c] += sum x^2                                   (BatchNorm statistics)
-// MODE 1: dz = dy * (act ? gelu'(z) : 1), z = xhat*gamma+beta; acc[0][c] += sum dz, acc[1][c] += sum dz*xhat (BN backward)
+// BatchNorm kernels. Thread block = (cvec channel-vectors) x (rows): threadIdx.x owns 8 consecutive channels for the whole
+// launch (per-channel parameters live in registers), threadIdx.y walks rows with a grid stride. A row of C channels is
+// cvec consecutive 16-byte vectors, so every warp access is contiguous for any C (48 ... 768).
+// MODE 0: acc[0][c] += sum x,  acc[1][c] += sum x^2                                   (statistics)
+// MODE 1: dz = dy * (act ? gelu'(z) : 1), z = xhat*gamma+beta; acc[0][c] += sum dz, acc[1][c] += sum dz*xhat (backward)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int BN_MAX_ROWS_PER_BLOCK = 64;
+
 template <int MODE>
 __global__ void __launch_bounds__(CV_THREADS) bn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                                               float* __restrict__ acc, long long M, int C, long long rows_per_block) {
-  __shared__ float red[2][CV_WARPS][256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
-  const long long r0 = (long long)blockIdx.y * rows_per_block;
-  const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+                                                               float* __restrict__ acc, long long M, int C, int cv0) {
+  extern __shared__ float bn_red[];   // [2][blockDim.y][blockDim.x * 8]
+  const int cv = cv0 + threadIdx.x;   // channel vector owned by this thread
+  const int c0 = cv * 8;
+  const int nx = blockDim.x, ny = blockDim.y;
   float a0[8], a1[8], mu[8], rs[8], g[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; mu[j] = 0.f; rs[j] = 1.f; g[j] = 1.f; b[j] = 0.f; }
-  if (c0 < C) {
-    if (MODE == 1) {
+  if (MODE == 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; g[j] = gamma[c0 + j]; b[j] = beta[c0 + j]; }
-    }
-    for (long long r = r0 + warp; r < r1; r += CV_WARPS) {
-      float xv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
-      if (MODE == 0) {
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; g[j] = gamma[c0 + j]; b[j] = beta[c0 + j]; }
+  }
+  for (long long r = (long long)blockIdx.x * ny + threadIdx.y; r < M; r += (long long)gridDim.x * ny) {
+    float xv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
+    if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
-      } else {
-        float dv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), dv);
+      for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
+    } else {
+      float dv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), dv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mu[j]) * rs[j];
-          float dz = dv[j];
-          if (act) dz *= cv_gelu_grad(fmaf(xh, g[j], b[j]));
-          a0[j] += dz;
-          a1[j] = fmaf(dz, xh, a1[j]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[j]) * rs[j];
+        float dz = dv[j];
+        if (act) dz *= cv_gelu_grad(fmaf(xh, g[j], b[j]));
+        a0[j] += dz;
+        a1[j] = fmaf(dz, xh, a1[j]);
       }
     }
   }
+  float* r0 = bn_red + (size_t)threadIdx.y * nx * 8 + threadIdx.x * 8;
+  float* r1 = r0 + (size_t)ny * nx * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { red[0][warp][lane * 8 + j] = a0[j]; red[1][warp][lane * 8 + j] = a1[j]; }
+  for (int j = 0; j < 8; ++j) { r0[j] = a0[j]; r1[j] = a1[j]; }
   __syncthreads();
-  const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < C) {
+  const int tid = threadIdx.y * nx + threadIdx.x;
+  for (int c = tid; c < nx * 8; c += nx * ny) {
     float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < CV_WARPS; ++w) { t0 += red[0][w][c]; t1 += red[1][w][c]; }
-    atomicAdd(acc + blockIdx.x * 256 + c, t0);
-    atomicAdd(acc + C + blockIdx.x * 256 + c, t1);
+    for (int q = 0; q < ny; ++q) { t0 += bn_red[(size_t)q * nx * 8 + c]; t1 += bn_red[(size_t)(ny + q) * nx * 8 + c]; }
+    atomicAdd(acc + cv0 * 8 + c, t0);
+    atomicAdd(acc + C + cv0 * 8 + c, t1);
   }
 }
 
@@ -128,26 +130,29 @@ __global__ void bn_finalize_kernel(const float* __restrict__ acc, float* __restr
 __global__ void __launch_bounds__(CV_THREADS) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
-                                                              __nv_bfloat16* __restrict__ y, long long M, int C, int act) {
-  const int cvec = C / 8;
-  const long long total = M * cvec;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c0 = (int)(i % cvec) * 8;
+                                                              __nv_bfloat16* __restrict__ y, long long M, int C, int act, int cv0) {
+  const int c0 = (cv0 + threadIdx.x) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = rstd[c0 + j] * gamma[c0 + j];
+    sh[j] = fmaf(-mean[c0 + j], sc[j], beta[c0 + j]);
+  }
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
     float xv[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf((xv[j] - __ldg(mean + c0 + j)) * __ldg(rstd + c0 + j), __ldg(gamma + c0 + j), __ldg(beta + c0 + j));
+      const float z = fmaf(xv[j], sc[j], sh[j]);
       o[j] = act ? cv_gelu(z) : z;
     }
     if (residual) {
       float rv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), rv);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(residual + r * C + c0)), rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += rv[j];
     }
-    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+    *reinterpret_cast<uint4*>(y + r * C + c0) = pack8(o);
   }
 }
 
@@ -157,42 +162,57 @@ __global__ void __launch_bounds__(CV_THREADS) bn_bwd_apply_kernel(const __nv_bfl
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ acc, __nv_bfloat16* __restrict__ dx,
                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C,
-                                                                  int act) {
-  const int cvec = C / 8;
-  const long long total = M * cvec;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+                                                                  int act, int cv0) {
+  const int c0 = (cv0 + threadIdx.x) * 8;
   const float inv_m = 1.0f / (float)M;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) atomicAdd(dbeta + c, acc[c]);
-      if (dgamma) atomicAdd(dgamma + c, acc[C + c]);
-    }
+  float mu[8], rs[8], g[8], b[8], s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; g[j] = gamma[c0 + j]; b[j] = beta[c0 + j];
+    s0[j] = acc[c0 + j] * inv_m; s1[j] = acc[C + c0 + j] * inv_m;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c0 = (int)(i % cvec) * 8;
-    float xv[8], dv[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), dv);
+  if (blockIdx.x == 0 && threadIdx.y == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float rs = __ldg(rstd + c0 + j), g = __ldg(gamma + c0 + j);
-      const float xh = (xv[j] - __ldg(mean + c0 + j)) * rs;
-      float dz = dv[j];
-      if (act) dz *= cv_gelu_grad(fmaf(xh, g, __ldg(beta + c0 + j)));
-      o[j] = g * rs * (dz - __ldg(acc + c0 + j) * inv_m - xh * __ldg(acc + C + c0 + j) * inv_m);
+      if (dbeta) atomicAdd(dbeta + c0 + j, acc[c0 + j]);
+      if (dgamma) atomicAdd(dgamma + c0 + j, acc[C + c0 + j]);
     }
-    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
+    float xv[8], dv[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv[j] - mu[j]) * rs[j];
+      float dz = dv[j];
+      if (act) dz *= cv_gelu_grad(fmaf(xh, g[j], b[j]));
+      o[j] = g[j] * rs[j] * (dz - s0[j] - xh * s1[j]);
+    }
+    *reinterpret_cast<uint4*>(dx + r * C + c0) = pack8(o);
   }
 }
 
-static inline void reduce_grid(long long M, int C, dim3& grid, long long& rows_per_block) {
-  const int col_blocks = (C + 255) / 256;
-  long long slabs = ((long long)num_sms() * 8 + col_blocks - 1) / col_blocks;
-  if (slabs > (M + 63) / 64) slabs = (M + 63) / 64;
-  if (slabs < 1) slabs = 1;
-  rows_per_block = (M + slabs - 1) / slabs;
-  grid = dim3(col_blocks, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+// launch geometry shared by the BatchNorm kernels: the channel vectors are split into chunks of <= 128 (blockDim.x),
+// blockDim.y rows per block so that a block has ~256 threads; one launch per chunk (1 for C <= 1024)
+struct BnLaunch {
+  dim3 block;
+  int grid;
+  size_t smem;
+};
+static inline BnLaunch bn_launch(long long M, int nx) {
+  BnLaunch l;
+  int ny = CV_THREADS / nx;
+  if (ny < 1) ny = 1;
+  if (ny > BN_MAX_ROWS_PER_BLOCK) ny = BN_MAX_ROWS_PER_BLOCK;
+  l.block = dim3(nx, ny);
+  long long g = (M + ny - 1) / ny;
+  const long long cap = (long long)num_sms() * 8;
+  l.grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
+  l.smem = (size_t)2 * ny * nx * 8 * sizeof(float);
+  return l;
 }
+
 static inline int ew_blocks(long long items) {
   long long g = (items + CV_THREADS - 1) / CV_THREADS;
   const long long cap = (long long)num_sms() * 16;
@@ -210,25 +230,36 @@ extern "C" int vmae_bn_train_fwd(const void* x, const float* gamma, const float*
   VMAE_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0, "vmae_bn_train_fwd: C=%d must be a positive multiple of 8", C);
   cudaStream_t s = (cudaStream_t)stream;
   VMAE_CUDA(cudaMemsetAsync(workspace, 0, 2 * (size_t)C * sizeof(float), s));
-  dim3 grid;
-  long long rpb;
-  reduce_grid(M, C, grid, rpb);
-  bn_reduce_kernel<0><<<grid, CV_THREADS, 0, s>>>((const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, workspace, M, C, rpb);
-  VMAE_LAUNCH_CHECK();
+  const int cvec = C / 8;
+  for (int cv0 = 0; cv0 < cvec; cv0 += 128) {
+    const int nx = (cvec - cv0 < 128) ? cvec - cv0 : 128;
+    const BnLaunch l = bn_launch(M, nx);
+    bn_reduce_kernel<0><<<l.grid, l.block, l.smem, s>>>((const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, workspace, M, C, cv0);
+    VMAE_LAUNCH_CHECK();
+  }
   bn_finalize_kernel<<<1, 256, 0, s>>>(workspace, mean, rstd, running_mean, running_var, M, C, eps, momentum);
   VMAE_LAUNCH_CHECK();
-  bn_apply_kernel<<<ew_blocks(M * (C / 8)), CV_THREADS, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (const __nv_bfloat16*)residual,
-                                                                (__nv_bfloat16*)y, M, C, act);
-  VMAE_LAUNCH_CHECK();
+  for (int cv0 = 0; cv0 < cvec; cv0 += 128) {
+    const int nx = (cvec - cv0 < 128) ? cvec - cv0 : 128;
+    const BnLaunch l = bn_launch(M, nx);
+    bn_apply_kernel<<<l.grid, l.block, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, M, C,
+                                               act, cv0);
+    VMAE_LAUNCH_CHECK();
+  }
   return VMAE_OK;
 }
 
 extern "C" int vmae_bn_apply(const void* x, const float* gamma, const float* beta, const float* mean, const float* rstd, const void* residual,
                              void* y, long long M, int C, int act, void* stream) {
   VMAE_CHECK_ARG(x && gamma && beta && mean && rstd && y && M > 0 && C > 0 && C % 8 == 0, "vmae_bn_apply: bad args");
-  bn_apply_kernel<<<ew_blocks(M * (C / 8)), CV_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta,
-                                                                                   (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, M, C, act);
-  VMAE_LAUNCH_CHECK();
+  const int cvec = C / 8;
+  for (int cv0 = 0; cv0 < cvec; cv0 += 128) {
+    const int nx = (cvec - cv0 < 128) ? cvec - cv0 : 128;
+    const BnLaunch l = bn_launch(M, nx);
+    bn_apply_kernel<<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (const __nv_bfloat16*)residual,
+                                                                  (__nv_bfloat16*)y, M, C, act, cv0);
+    VMAE_LAUNCH_CHECK();
+  }
   return VMAE_OK;
 }
 
@@ -238,14 +269,21 @@ extern "C" int vmae_bn_train_bwd(const void* x, const void* dy, const float* gam
   VMAE_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0, "vmae_bn_train_bwd: C=%d must be a positive multiple of 8", C);
   cudaStream_t s = (cudaStream_t)stream;
   VMAE_CUDA(cudaMemsetAsync(workspace, 0, 2 * (size_t)C * sizeof(float), s));
-  dim3 grid;
-  long long rpb;
-  reduce_grid(M, C, grid, rpb);
-  bn_reduce_kernel<1><<<grid, CV_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd, gamma, beta, act, workspace, M, C, rpb);
-  VMAE_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_blocks(M * (C / 8)), CV_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd, gamma, beta,
-                                                                    workspace, (__nv_bfloat16*)dx, dgamma, dbeta, M, C, act);
-  VMAE_LAUNCH_CHECK();
+  const int cvec = C / 8;
+  for (int cv0 = 0; cv0 < cvec; cv0 += 128) {
+    const int nx = (cvec - cv0 < 128) ? cvec - cv0 : 128;
+    const BnLaunch l = bn_launch(M, nx);
+    bn_reduce_kernel<1><<<l.grid, l.block, l.smem, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd, gamma, beta, act, workspace, M, C,
+                                                        cv0);
+    VMAE_LAUNCH_CHECK();
+  }
+  for (int cv0 = 0; cv0 < cvec; cv0 += 128) {
+    const int nx = (cvec - cv0 < 128) ? cvec - cv0 : 128;
+    const BnLaunch l = bn_launch(M, nx);
+    bn_bwd_apply_kernel<<<l.grid, l.block, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd, gamma, beta, workspace,
+                                                   (__nv_bfloat16*)dx, dgamma, dbeta, M, C, act, cv0);
+    VMAE_LAUNCH_CHECK();
+  }
   return VMAE_OK;
 }
 
