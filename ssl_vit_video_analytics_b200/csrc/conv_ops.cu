@@ -307,11 +307,12 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const __nv_bfloat16* __
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int t = 0; t < 9; ++t) wt[t][j] = __ldg(w + (c0 + j) * 9 + t);
-  const long long npix = (long long)g.N * g.Ho * g.Wo;
-  for (long long p = (long long)blockIdx.y * 16 + threadIdx.y; p < npix; p += (long long)gridDim.y * 16) {
-    const int wo = (int)(p % g.Wo);
-    const int ho = (int)((p / g.Wo) % g.Ho);
-    const int n = (int)(p / ((long long)g.Wo * g.Ho));
+  const int npix = g.N * g.Ho * g.Wo;   // < 2^31 (checked on the host): 32-bit index arithmetic, 64-bit only for byte offsets
+  for (int p = blockIdx.y * 16 + threadIdx.y; p < npix; p += gridDim.y * 16) {
+    const int wo = p % g.Wo;
+    const int t_ = p / g.Wo;
+    const int ho = t_ % g.Ho;
+    const int n = t_ / g.Ho;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const __nv_bfloat16* __
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wt[kh * 3 + kw][j], acc[j]);
       }
     }
-    *reinterpret_cast<uint4*>(y + p * g.C + c0) = pack8(acc);
+    *reinterpret_cast<uint4*>(y + (long long)p * g.C + c0) = pack8(acc);
   }
 }
 
@@ -343,11 +344,12 @@ __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const __nv_bfloat16* 
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int t = 0; t < 9; ++t) wt[t][j] = __ldg(w + (c0 + j) * 9 + t);
-  const long long npix = (long long)g.N * g.H * g.W;
-  for (long long p = (long long)blockIdx.y * 16 + threadIdx.y; p < npix; p += (long long)gridDim.y * 16) {
-    const int wi = (int)(p % g.W);
-    const int hi = (int)((p / g.W) % g.H);
-    const int n = (int)(p / ((long long)g.W * g.H));
+  const int npix = g.N * g.H * g.W;
+  for (int p = blockIdx.y * 16 + threadIdx.y; p < npix; p += gridDim.y * 16) {
+    const int wi = p % g.W;
+    const int t_ = p / g.W;
+    const int hi = t_ % g.H;
+    const int n = t_ / g.H;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const __nv_bfloat16* 
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[j], wt[kh * 3 + kw][j], acc[j]);
       }
     }
-    *reinterpret_cast<uint4*>(dx + p * g.C + c0) = pack8(acc);
+    *reinterpret_cast<uint4*>(dx + (long long)p * g.C + c0) = pack8(acc);
   }
 }
 
@@ -386,14 +388,15 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const __nv_bfloat16* 
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-  const long long npix = (long long)g.N * g.Ho * g.Wo;
+  const int npix = g.N * g.Ho * g.Wo;
   if (live) {
-    for (long long p = (long long)blockIdx.y * 16 + threadIdx.y; p < npix; p += (long long)gridDim.y * 16) {
-      const int wo = (int)(p % g.Wo);
-      const int ho = (int)((p / g.Wo) % g.Ho);
-      const int n = (int)(p / ((long long)g.Wo * g.Ho));
+    for (int p = blockIdx.y * 16 + threadIdx.y; p < npix; p += gridDim.y * 16) {
+      const int wo = p % g.Wo;
+      const int t_ = p / g.Wo;
+      const int ho = t_ % g.Ho;
+      const int n = t_ / g.Ho;
       float dv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + p * g.C + c0)), dv);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (long long)p * g.C + c0)), dv);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int hi = ho * g.stride + kh - 1;
@@ -582,7 +585,7 @@ static inline dim3 dw_grid(int C, long long npix) {
 using namespace vmae;
 
 static int dw_geom(DwGeom& g, int N, int H, int W, int C, int stride, const char* who) {
-  if (!(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2)))
+  if (!(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2) && (long long)N * H * W < (1ll << 31)))
     return fail(VMAE_ERR_BAD_ARG, "%s: bad geometry N=%d H=%d W=%d C=%d stride=%d (C %% 8 == 0, stride 1|2)", who, N, H, W, C, stride);
   g.N = N; g.H = H; g.W = W; g.C = C; g.stride = stride;
   g.Ho = (H + 2 - 3) / stride + 1;
