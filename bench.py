@@ -326,8 +326,14 @@ def run_ours(args, cfg):
     dom = max((k for k in tensor_classes if k in prof), key=lambda k: prof[k]["ms"])
     d = prof[dom]
     achieved = d["work"] / (d["ms"] / 1e3) / 1e12
+    traffic = None
+    try:   # DRAM bytes per launch of that kernel class from the committed `ncu --set full` capture (same shapes)
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom) if args.workload == "vit_s" else None
+    except OSError:
+        pass
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_per_step": d["launches"], "ms_per_step": d["ms"],
                 "step_frac_of_tensor_roofline": (B * step_gflop / 1e3) / (ms_step / 1e3) / peaks["bf16_tflops_sustained"],
                 "by_kernel_class": {k: {"ms_per_step": round(v["ms"], 3), "launches_per_step": v["launches"],
