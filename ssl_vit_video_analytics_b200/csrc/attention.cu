@@ -17,10 +17,33 @@
 
 namespace vmae {
 
-constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 UMMA, warps 2..5 one thread per row
+#ifdef VMAE_ATT_TRACE
+// developer timeline (tools/trace_attn.cu): clock64 stamps of one CTA, [role 0 = row warp 2 lane 0 | 1 = MMA thread][iteration][slot]
+__device__ long long g_att_trace[2 * 32 * 8];
+__device__ int g_att_trace_cta[4];   // block x, y, z, backward mode filter (-1 = any)
+#define ATT_TRACE_INIT()                                                                                               \
+  const bool att_traced = blockIdx.x == g_att_trace_cta[0] && blockIdx.y == g_att_trace_cta[1] && blockIdx.z == g_att_trace_cta[2]
+#define ATT_STAMP(role, it, slot)                                                                                      \
+  do {                                                                                                                 \
+    if (att_traced && (it) < 32 && ((role) == 1 || threadIdx.x == 128)) g_att_trace[((role) * 32 + (it)) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define ATT_TRACE_INIT() do { } while (0)
+#define ATT_STAMP(role, it, slot) do { } while (0)
+#endif
+
+constexpr int ATT_FWD_THREADS = 256;  // all kernels: warpgroup 0 = control (warp 0 UMMA issuer, warp 1 TMA producer), warpgroup 1 = one thread per row
+// Two CTAs per SM leave 128 registers per thread at launch; the control warpgroup shrinks to ATT_CTRL_REGS and the row
+// warpgroup grows to ATT_ROW_REGS (setmaxnreg), enough to keep a whole 128-column score row in registers.
+constexpr int ATT_CTRL_REGS = 40;
+constexpr int ATT_ROW_REGS = 216;
+static_assert(ATT_CTRL_REGS + ATT_ROW_REGS <= 256, "per-CTA register pool: 256 threads x 128");
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2; exp2f() costs ~10 instructions (denormal handling)
+#ifdef VMAE_ATT_NOEXP   // developer experiment: how much of the kernel time is the MUFU pipe? (wrong numerics)
+  return x * 0.001f + 0.5f;
+#endif
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -80,10 +103,11 @@ struct FwdCfg {
 };
 
 template <int HD, int BKV>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale) {
   using Cfg = FwdCfg<HD, BKV>;
+  static_assert(BKV == 128, "the row threads hold one 128-column score row in registers");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   check_smem_alignment(smem_raw);
   const uint32_t sbase = smem_u32(smem_raw);
@@ -92,7 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   auto sK = [&](int s) { return sbase + Cfg::OFF_K + s * Cfg::KV_BYTES; };
   auto sV = [&](int s) { return sbase + Cfg::OFF_V + s * Cfg::KV_BYTES; };
   const uint32_t bar = sbase + Cfg::OFF_BAR;
-  const uint32_t q_full = bar, s_full = bar + 8, p_ready = bar + 16, o_full = bar + 24;
+  const uint32_t q_full = bar, s_full = bar + 8, p_ready = bar + 16, o_full = bar + 24, s_free = bar + 104;
   auto kv_full = [&](int s) { return bar + 32 + 8 * s; };
   auto kv_empty = [&](int s) { return bar + 64 + 8 * s; };
   const uint32_t tmem_ptr_addr = bar + 96;
@@ -101,6 +125,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (L + BKV - 1) / BKV;
+  ATT_TRACE_INIT();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
@@ -108,19 +133,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
+    mbar_init(s_free, 4);
     mbar_init(o_full, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tS = tmem, tO = tmem + BKV, tP = tmem + BKV + HD;   // P: bf16 A-operand, BKV/2 packed columns
 
-  if (warp == 0) {
-    if (elect_one()) {
+  if (warp < 4) {
+    setmaxnreg_dec<ATT_CTRL_REGS>();
+    if (warp == 1 && elect_one()) {   // TMA producer
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
       tma_load_3d(sQ, &map_q, q_full, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
@@ -130,9 +157,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tma_load_3d(sK(s), &map_kv, kv_full(s), (H + h) * HD, j * BKV, b);
         tma_load_3d(sV(s), &map_kv, kv_full(s), (2 * H + h) * HD, j * BKV, b);
       }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
+    } else if (warp == 0 && elect_one()) {   // UMMA issuer
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       // descriptor bases are built once; inside the loops only the 14-bit start-address field advances (bytes >> 4).
@@ -156,18 +181,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         const int s = j % NS;
-        mbar_wait(p_ready, j & 1);   // rows have consumed S_j and written P_j (bf16, in TMEM)
+        ATT_STAMP(1, j, 0);
+        if (j + 1 < nkv) {   // the rows hold S_j in registers: compute S_{j+1} underneath their softmax
+          mbar_wait(s_free, j & 1);
+          tc_fence_after();
+          ATT_STAMP(1, j, 1);
+          issue_s(j + 1);
+        }
+        ATT_STAMP(1, j, 2);
+        mbar_wait(p_ready, j & 1);   // P_j (bf16) is in TMEM
         tc_fence_after();
-        if (j + 1 < nkv) issue_s(j + 1);  // next scores first: the rows get S_{j+1} while P_j V_j is still being issued
+        ATT_STAMP(1, j, 3);
         // O += P_j V_j with P read straight from TMEM (TS form): P never touches shared memory
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
           umma_bf16_ts(tO, tP + kk * 8, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
         umma_commit(o_full);
         umma_commit(kv_empty(s));
+        ATT_STAMP(1, j, 4);
       }
     }
   } else {
+    setmaxnreg_inc<ATT_ROW_REGS>();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -177,33 +212,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // stale reference is kept (P <= 256 stays exact enough in bf16 and l / O carry the same factor, which cancels).
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
+      ATT_STAMP(0, j, 0);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int valid = min(BKV, L - j * BKV);
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + c * 32, r);
-        tmem_wait_ld();
-        if (valid == BKV) {
+      ATT_STAMP(0, j, 1);
+      // The whole score row goes to registers with four back-to-back TMEM loads and ONE wait (a load + wait pair costs
+      // ~160 cycles, four pipelined loads ~280), and S is read once instead of twice. As soon as the loads have landed
+      // the S columns are free again: the MMA warp computes S_{j+1} underneath this block's softmax.
+      uint32_t sc[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_off + c * 32, sc[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(s_free);
+      ATT_STAMP(0, j, 2);
+      const int valid = min(BKV, L - j * BKV);
+      if (valid < BKV) {   // ragged last block: columns past the sequence end never win the max and give p == 0
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+            if (c * 32 + i >= valid) sc[c][i] = 0xff800000u;   // -inf
       }
-      if (j > 0) {  // P_{j-1} V_{j-1} has retired: O is stable and the P region of TMEM may be overwritten
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = __uint_as_float(sc[c][0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mx4[c] = fmaxf(mx4[c], __uint_as_float(sc[c][i]));
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (j == 0) {
         m = mx;
       } else {
         const bool need = (mx - m) * sl2 > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(o_full, (j - 1) & 1);   // P_{j-1} V_{j-1} has retired: O is stable
+          tc_fence_after();
           const float m_new = need ? mx : m;
           const float alpha = ex2_approx((m - m_new) * sl2);  // exactly 1 for rows that keep their reference
           m = m_new;
@@ -221,31 +266,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
       const float msl = m * sl2;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + c * 32, r);
-        tmem_wait_ld();
-        float p[32];
-        if (valid == BKV) {
+      ATT_STAMP(0, j, 3);
+      ATT_STAMP(0, j, 4);
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
-            l += p[i];
-          }
-        } else {
+      for (int c = 0; c < 4; ++c) {
+        // packed in place (slot i/2 has already been consumed when pair i is written): no second register array
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl)) : 0.f;
-            l += p[i];
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sc[c][i]), sl2, -msl));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sc[c][i + 1]), sl2, -msl));
+          l4[c] += p0 + p1;
+          sc[c][i >> 1] = pack_bf16x2(p0, p1);
         }
-        store_tmem_operand32(tP + lane_off + c * 16, p);
       }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      // P_j stays in registers until P_{j-1} V_{j-1} has retired (its P operand and its K/V stage are then free). Waiting
+      // here instead of before the exponentials takes the MMA round trip (observe p_ready, issue, execute behind the
+      // other CTA's MMAs, commit) off the critical path: by now it finished ~1000 cycles ago.
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(tP + lane_off + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sc[c][0]));
+      ATT_STAMP(0, j, 5);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);   // one arrival per warp: mbarrier operations serialise
+      ATT_STAMP(0, j, 6);
     }
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
@@ -273,7 +323,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
 }
 
 // ======================================================================================================================
@@ -317,25 +367,32 @@ struct BwdCfg {
   static constexpr int Y_BYTES = BS * ROWB;    // streamed tile
   static constexpr int E_BYTES = 128 * BS * 2; // bf16 operand tile written by the row threads
   static constexpr int NUM_E = (MODE == BWD_DKDV) ? 2 : 1;
+  static constexpr int NS = 3;                 // streamed-tile ring depth
   static constexpr int OFF_R0 = 0;
   static constexpr int OFF_R1 = OFF_R0 + R_BYTES;
-  static constexpr int OFF_Y = OFF_R1 + R_BYTES;           // [2 stages][2 tiles]
-  static constexpr int OFF_E = OFF_Y + 4 * Y_BYTES;        // [NUM_E]
-  static constexpr int OFF_STAT = OFF_E + NUM_E * E_BYTES; // [2][2][BS] floats (DKDV only)
-  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * BS * 4;
+  static constexpr int OFF_Y = OFF_R1 + R_BYTES;           // [NS stages][2 tiles]
+  static constexpr int OFF_E = OFF_Y + NS * 2 * Y_BYTES;   // [NUM_E]
+  static constexpr int OFF_STAT = OFF_E + NUM_E * E_BYTES; // [2][BS] floats: lse*log2(e) and delta of the streamed query block (dK/dV)
+  static constexpr int OFF_BAR = OFF_STAT + (MODE == BWD_DKDV ? 2 * BS * 4 : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static_assert(SMEM_BYTES <= 115712, "two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2");
   static constexpr int TMEM_NEED = 2 * BS + NUM_E * HD;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
 };
 
 // map_res_* have 128-row boxes (resident tiles), map_str_* have BS-row boxes (streamed tiles).
+// 256 threads: warpgroup 0 = control (warp 0 UMMA issuer, warp 1 TMA producer), warpgroup 1 = one thread per row. As in the
+// forward, the row threads pull both score-like tiles of an iteration into registers with back-to-back TMEM loads and
+// hand the TMEM columns straight back, so T(it+1) is computed underneath the element-wise phase of iteration it.
 template <int HD, int BS, int MODE>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_constant__ CUtensorMap map_str_qkv,
                 const __grid_constant__ CUtensorMap map_res_do, const __grid_constant__ CUtensorMap map_str_do,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int H,
                 float scale) {
   using Cfg = BwdCfg<HD, BS, MODE>;
+  static_assert(BS == 64, "the row threads hold two 64-column tiles in registers");
+  constexpr int NS = Cfg::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   check_smem_alignment(smem_raw);
   const uint32_t sbase = smem_u32(smem_raw);
@@ -344,15 +401,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
   auto sE = [&](int t) { return sbase + Cfg::OFF_E + t * Cfg::E_BYTES; };
   float* stat = reinterpret_cast<float*>(smem_raw + Cfg::OFF_STAT);
   const uint32_t bar = sbase + Cfg::OFF_BAR;
-  const uint32_t res_full = bar, t_full = bar + 8, e_ready = bar + 16, e_free = bar + 24, acc_full = bar + 32;
-  auto st_full = [&](int s) { return bar + 40 + 8 * s; };
-  auto st_empty = [&](int s) { return bar + 56 + 8 * s; };
-  const uint32_t tmem_ptr_addr = bar + 72;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 72);
+  const uint32_t res_full = bar, t_full = bar + 8, t_free = bar + 16, e_ready = bar + 24, e_free = bar + 32, acc_full = bar + 40;
+  auto st_full = [&](int s) { return bar + 48 + 8 * s; };
+  auto st_empty = [&](int s) { return bar + 72 + 8 * s; };
+  const uint32_t tmem_ptr_addr = bar + 96;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int niter = (L + BS - 1) / BS;
+#ifdef VMAE_ATT_TRACE
+  const bool att_traced = blockIdx.x == g_att_trace_cta[0] && blockIdx.y == g_att_trace_cta[1] && blockIdx.z == g_att_trace_cta[2] &&
+                          (g_att_trace_cta[3] < 0 || g_att_trace_cta[3] == MODE);
+#endif
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_res_qkv);
@@ -361,21 +422,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
     tma_prefetch_desc(&map_str_do);
     mbar_init(res_full, 1);
     mbar_init(t_full, 1);
+    mbar_init(t_free, 4);
     mbar_init(e_ready, 4);
     mbar_init(e_free, 1);
     mbar_init(acc_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tT0 = tmem, tT1 = tmem + BS, tA0 = tmem + 2 * BS, tA1 = tmem + 2 * BS + HD;
 
-  if (warp == 0) {
-    if (elect_one()) {
+  if (warp < 4) {
+    setmaxnreg_dec<ATT_CTRL_REGS>();
+    if (warp == 1 && elect_one()) {   // TMA producer
       mbar_expect_tx(res_full, 2 * Cfg::R_BYTES);
       if (MODE == BWD_DQ) {
         tma_load_3d(sR0, &map_res_qkv, res_full, h * HD, r0, b);          // Q
@@ -385,8 +448,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
         tma_load_3d(sR1, &map_res_qkv, res_full, (2 * H + h) * HD, r0, b);// V
       }
       for (int it = 0; it < niter; ++it) {
-        const int s = it & 1;
-        mbar_wait(st_empty(s), ((it >> 1) & 1) ^ 1u);
+        const int s = it % NS;
+        mbar_wait(st_empty(s), ((it / NS) & 1) ^ 1u);
         mbar_expect_tx(st_full(s), 2 * Cfg::Y_BYTES);
         if (MODE == BWD_DQ) {
           tma_load_3d(sY(s, 0), &map_str_qkv, st_full(s), (H + h) * HD, it * BS, b);      // K_j
@@ -396,19 +459,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
           tma_load_3d(sY(s, 1), &map_str_do, st_full(s), h * HD, it * BS, b);             // dO_i
         }
       }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
+    } else if (warp == 0 && elect_one()) {   // UMMA issuer
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, BS, 0, 0);
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);
       // descriptor bases are built once; inside the loops only the 14-bit start-address field advances (bytes >> 4)
       const uint64_t dR0 = umma_smem_desc(sR0, 0, 8 * Cfg::ROWB, Cfg::ROWB), dR1 = umma_smem_desc(sR1, 0, 8 * Cfg::ROWB, Cfg::ROWB);
-      const uint64_t dY0[2] = {umma_smem_desc(sY(0, 0), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sY(1, 0), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
-      const uint64_t dY1[2] = {umma_smem_desc(sY(0, 1), 0, 8 * Cfg::ROWB, Cfg::ROWB), umma_smem_desc(sY(1, 1), 0, 8 * Cfg::ROWB, Cfg::ROWB)};
+      uint64_t dY0[NS], dY1[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        dY0[s] = umma_smem_desc(sY(s, 0), 0, 8 * Cfg::ROWB, Cfg::ROWB);
+        dY1[s] = umma_smem_desc(sY(s, 1), 0, 8 * Cfg::ROWB, Cfg::ROWB);
+      }
       const uint64_t dE0 = umma_smem_desc(sE(0), 0, 1024, 128), dE1 = umma_smem_desc(sE(1), 0, 1024, 128);
       auto issue_t = [&](int it) {
-        const int s = it & 1;
-        mbar_wait(st_full(s), (it >> 1) & 1);
+        const int s = it % NS;
+        mbar_wait(st_full(s), (it / NS) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tT0, dR0 + 2 * k, dY0[s] + 2 * k, idesc_t, k > 0);
@@ -419,10 +484,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
       mbar_wait(res_full, 0);
       issue_t(0);
       for (int it = 0; it < niter; ++it) {
-        const int s = it & 1;
-        mbar_wait(e_ready, it & 1);   // rows have consumed T(it) and written E(it)
+        const int s = it % NS;
+        ATT_STAMP(1, it, 0);
+        if (it + 1 < niter) {   // the rows hold T(it) in registers: compute T(it+1) underneath their element-wise phase
+          mbar_wait(t_free, it & 1);
+          tc_fence_after();
+          ATT_STAMP(1, it, 1);
+          issue_t(it + 1);
+        }
+        ATT_STAMP(1, it, 2);
+        mbar_wait(e_ready, it & 1);   // E(it) is in shared memory
         tc_fence_after();
-        if (it + 1 < niter) issue_t(it + 1);  // next score tiles first: they are on the rows' critical path
+        ATT_STAMP(1, it, 3);
 #pragma unroll
         for (int kk = 0; kk < BS / 16; ++kk)  // ACC0 += E0 * Y0 (Y0 read as an MN-major B operand: rows = contraction index)
           umma_bf16(tA0, dE0 + 2 * kk, dY0[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_a, (it > 0 || kk > 0));
@@ -433,13 +506,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
         }
         umma_commit(st_empty(s));
         umma_commit(e_free);
+        ATT_STAMP(1, it, 4);
       }
       umma_commit(acc_full);
     }
   } else {
+    setmaxnreg_inc<ATT_ROW_REGS>();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int tid = threadIdx.x - 64;  // 0..127 among the row threads
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float sl2 = scale * LOG2E;
     const int g_row = r0 + row;
@@ -449,53 +523,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
       lse_row = lse[stat_base + g_row] * LOG2E;
       delta_row = delta[stat_base + g_row];
     }
-    if (MODE == BWD_DKDV && tid < 2 * BS) {
-      const int g = tid % BS;
+    // dK/dV: the statistics of the streamed query block (one lse and one delta per column) are the same for every thread.
+    // They live in one 512-byte shared buffer: each row thread fetches one value of the NEXT block at the top of an
+    // iteration (global-load latency hidden behind the iteration) and deposits it once everybody has finished reading
+    // the current block. Columns past the sequence end get lse = +inf, i.e. p == 0 without a predicate.
+    const int tid = threadIdx.x - 128;
+    const float stat_mul = (tid < BS) ? LOG2E : 1.0f;   // applied when the value is deposited: the load must not be consumed early
+    auto fetch_stat = [&](int it) {
+      const int g = it * BS + (tid & (BS - 1));
       float v = (tid < BS) ? INFINITY : 0.f;
-      if (g < L) v = (tid < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
-      stat[tid] = v;
-    }
+      if (g < L) v = __ldg(((tid < BS) ? lse : delta) + stat_base + g);
+      return v;
+    };
+    if (MODE == BWD_DKDV) stat[tid] = fetch_stat(0) * stat_mul;
     for (int it = 0; it < niter; ++it) {
       const int valid = min(BS, L - it * BS);
-      float* st_lse = stat + (it & 1) * 2 * BS;
-      float* st_delta = st_lse + BS;
       float stat_next = 0.f;
-      if (MODE == BWD_DKDV) {
-        named_bar_sync(1, 128);   // statistics of this iteration (written during the previous one) are visible
-        // prefetch the column statistics of the NEXT streamed query block (global-load latency hidden behind this iteration);
-        // out-of-range columns get lse = +inf so that p == 0 there
-        if (tid < 2 * BS && it + 1 < niter) {
-          const int g = (it + 1) * BS + (tid % BS);
-          stat_next = (tid < BS) ? INFINITY : 0.f;
-          if (g < L) stat_next = (tid < BS) ? lse[stat_base + g] * LOG2E : delta[stat_base + g];
-        }
-      }
+      if (MODE == BWD_DKDV && it + 1 < niter) stat_next = fetch_stat(it + 1);
+      ATT_STAMP(0, it, 0);
       mbar_wait(t_full, it & 1);
       tc_fence_after();
-      if (it > 0) mbar_wait(e_free, (it - 1) & 1);
-#pragma unroll 1
-      for (int c = 0; c < BS / 32; ++c) {
-        uint32_t rs[32], rp[32];
-        tmem_ld32(tT0 + lane_off + c * 32, rs);
-        tmem_ld32(tT1 + lane_off + c * 32, rp);
-        tmem_wait_ld();
-        float ds[32], pp[32];
-        if (MODE == BWD_DQ) {
-          if (valid == BS) {
+      ATT_STAMP(0, it, 1);
+      uint32_t ts[2][32], tp[2][32];   // T0 (scores) and T1 (dP-like) of this row: 2 x 64 fp32
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row));
-              ds[i] = p * (__uint_as_float(rp[i]) - delta_row);
-            }
-          } else {
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tT0 + lane_off + c * 32, ts[c]);
+        tmem_ld32(tT1 + lane_off + c * 32, tp[c]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(t_free);
+      ATT_STAMP(0, it, 2);
+      // p -> ts (in place), ds -> tp (in place)
+      if (MODE == BWD_DQ) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float p = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lse_row)) : 0.f;
-              ds[i] = p * (__uint_as_float(rp[i]) - delta_row);
-            }
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float p = ex2_approx(fmaf(__uint_as_float(ts[c][i]), sl2, -lse_row));
+            if (valid < BS && c * 32 + i >= valid) p = 0.f;
+            tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - delta_row));
           }
-        } else {
-          // out-of-range query columns carry lse = +inf in the staged statistics, so p == 0 there without a predicate
+      } else {
+        named_bar_sync(1, 128);   // the statistics deposited at the end of the previous iteration are visible
+        const float* st_lse = stat;
+        const float* st_delta = stat + BS;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
             const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c * 32 + 4 * i4);
@@ -505,20 +579,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int i = 4 * i4 + t;
-              const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -lv[t]));
-              ds[i] = p * (__uint_as_float(rp[i]) - dv[t]);
-              pp[i] = p;
+              const float p = ex2_approx(fmaf(__uint_as_float(ts[c][i]), sl2, -lv[t]));
+              ts[c][i] = __float_as_uint(p);
+              tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - dv[t]));
             }
           }
-        }
-        store_tile_row32(sE(0), row, c * 32, ds);
-        if (MODE == BWD_DKDV) store_tile_row32(sE(1), row, c * 32, pp);
+        named_bar_sync(1, 128);   // everybody has read this block's statistics
+        stat[tid] = stat_next * stat_mul;
       }
-      if (MODE == BWD_DKDV && tid < 2 * BS && it + 1 < niter) (stat + ((it + 1) & 1) * 2 * BS)[tid] = stat_next;
+      ATT_STAMP(0, it, 3);
+      if (it > 0) mbar_wait(e_free, (it - 1) & 1);   // the MMAs that read E(it-1) have retired
+      ATT_STAMP(0, it, 4);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        store_tile_row32(sE(0), row, c * 32, reinterpret_cast<const float(&)[32]>(tp[c]));
+        if (MODE == BWD_DKDV) store_tile_row32(sE(1), row, c * 32, reinterpret_cast<const float(&)[32]>(ts[c]));
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(e_ready);   // one arrival per warp: mbarrier operations serialise
+      ATT_STAMP(0, it, 5);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -552,7 +633,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
 }
 
 static int make_map_rows(CUtensorMap* m, const void* base, int B, int L, int width, int hd, int box_rows) {
@@ -573,7 +654,7 @@ static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   auto kern = attn_fwd_kernel<HD, BKV>;
   VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((L + 127) / 128, H, B);
-  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale);
+  kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
@@ -594,7 +675,7 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
   auto kern = attn_bwd_kernel<HD, BS, MODE>;
   VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((L + 127) / 128, H, B);
-  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H, scale);
+  kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H, scale);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
@@ -602,6 +683,16 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
 }  // namespace vmae
 
 using namespace vmae;
+
+#ifdef VMAE_ATT_TRACE
+extern "C" int vmae_att_trace_select(int bx, int by, int bz, int mode) {
+  int h[4] = {bx, by, bz, mode};
+  cudaMemcpyToSymbol(g_att_trace_cta, h, sizeof(h));
+  static long long zero[2 * 32 * 8] = {0};
+  return (int)cudaMemcpyToSymbol(g_att_trace, zero, sizeof(zero));
+}
+extern "C" int vmae_att_trace_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_att_trace, sizeof(long long) * 2 * 32 * 8); }
+#endif
 
 extern "C" int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream) {
   VMAE_CHECK_ARG(qkv && out && lse, "vmae_attn_fwd: null pointer");
