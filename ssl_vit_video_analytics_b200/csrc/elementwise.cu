@@ -27,6 +27,18 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// "raw" 4-element vectors: what a prefetch holds in registers before it is converted (bf16 stays packed: half the registers)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+__device__ __forceinline__ float4 ldraw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint2 ldraw4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 cvt4(float4 v) { return v; }
+__device__ __forceinline__ float4 cvt4(uint2 u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 template <typename T>
 __device__ __forceinline__ void store4(T* p, float4 v);
 template <>
@@ -64,16 +76,32 @@ __global__ void __launch_bounds__(EW_THREADS) layernorm_fwd_kernel(const XT* __r
     }
   }
   const float inv_n = 1.0f / (float)cols;
+  // software pipeline: the loads of this warp's NEXT row are issued before the current row is reduced, so a warp keeps two
+  // rows of HBM traffic in flight instead of stalling on one (the kernel is latency-, not bandwidth-limited otherwise)
+  typename Raw4<XT>::type nxt[NV];
+  if (warp_global < rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < cols) nxt[i] = ldraw4(x + warp_global * cols + c);
+    }
+  }
   for (long long r = warp_global; r < rows; r += warp_stride) {
-    const XT* xr = x + r * cols;
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < cols) {
-        v[i] = load4<XT>(xr + c);
+        v[i] = cvt4(nxt[i]);
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    if (r + warp_stride < rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) nxt[i] = ldraw4(x + (r + warp_stride) * cols + c);
       }
     }
     const float mean = warp_sum(s) * inv_n;
@@ -112,7 +140,7 @@ __global__ void __launch_bounds__(EW_THREADS) layernorm_fwd_kernel(const XT* __r
 // gradient if given. dgamma/dbeta: per-lane register partials -> smem cross-warp reduce -> one red.add per column/CTA.
 // ------------------------------------------------------------------------------------------------------------------
 template <typename DT, typename XT, int NV>
-__global__ void __launch_bounds__(EW_THREADS, (NV <= 3) ? 3 : ((NV <= 4) ? 2 : 1)) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
+__global__ void __launch_bounds__(EW_THREADS, (NV <= 4) ? 2 : 1) layernorm_bwd_kernel(const DT* __restrict__ dy, const XT* __restrict__ x,
                                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ dx_resid,
                                                                    float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_out_bf16,
@@ -132,16 +160,37 @@ __global__ void __launch_bounds__(EW_THREADS, (NV <= 3) ? 3 : ((NV <= 4) ? 2 : 1
     if (c < cols) g[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
   }
   const float inv_n = 1.0f / (float)cols;
+  // software pipeline (see the forward): x, dy, the residual gradient and the row statistics of the NEXT row are requested
+  // before the current row is reduced
+  typename Raw4<XT>::type nx[NV];
+  typename Raw4<DT>::type nd[NV];
+  float4 nr[NV];
+  float nmu = 0.f, nrs = 0.f;
+  auto prefetch = [&](long long r) {
+    nmu = __ldg(mean + r);
+    nrs = __ldg(rstd + r);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < cols) {
+        nx[i] = ldraw4(x + r * cols + c);
+        nd[i] = ldraw4(dy + r * cols + c);
+        if (dx_resid) nr[i] = __ldg(reinterpret_cast<const float4*>(dx_resid + r * cols + c));
+      }
+    }
+  };
+  if (warp_global < rows) prefetch(warp_global);
   for (long long r = warp_global; r < rows; r += warp_stride) {
-    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float4 xh[NV], d[NV];
+    const float mu = nmu, rs = nrs;
+    float4 xh[NV], d[NV], rv[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < cols) {
-        const float4 xv = load4<XT>(x + r * cols + c);
-        d[i] = load4<DT>(dy + r * cols + c);
+        const float4 xv = cvt4(nx[i]);
+        d[i] = cvt4(nd[i]);
+        if (dx_resid) rv[i] = nr[i];
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         const float g0 = d[i].x * g[i].x, g1 = d[i].y * g[i].y, g2 = d[i].z * g[i].z, g3 = d[i].w * g[i].w;
         s1 += (g0 + g1) + (g2 + g3);
@@ -151,6 +200,7 @@ __global__ void __launch_bounds__(EW_THREADS, (NV <= 3) ? 3 : ((NV <= 4) ? 2 : 1
         acc_b[i].x += d[i].x; acc_b[i].y += d[i].y; acc_b[i].z += d[i].z; acc_b[i].w += d[i].w;
       }
     }
+    if (r + warp_stride < rows) prefetch(r + warp_stride);
     const float c1 = warp_sum(s1) * inv_n;
     const float c2 = warp_sum(s2) * inv_n;
 #pragma unroll
@@ -162,10 +212,7 @@ __global__ void __launch_bounds__(EW_THREADS, (NV <= 3) ? 3 : ((NV <= 4) ? 2 : 1
         o.y = rs * (d[i].y * g[i].y - c1 - xh[i].y * c2);
         o.z = rs * (d[i].z * g[i].z - c1 - xh[i].z * c2);
         o.w = rs * (d[i].w * g[i].w - c1 - xh[i].w * c2);
-        if (dx_resid) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(dx_resid + r * cols + c));
-          o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-        }
+        if (dx_resid) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
         if (dx_out) *reinterpret_cast<float4*>(dx_out + r * cols + c) = o;
         if (dx_out_bf16) store4<__nv_bfloat16>(dx_out_bf16 + r * cols + c, o);
       }
