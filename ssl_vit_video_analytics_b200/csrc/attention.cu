@@ -367,7 +367,7 @@ struct BwdCfg {
   static constexpr int Y_BYTES = BS * ROWB;    // streamed tile
   static constexpr int E_BYTES = 128 * BS * 2; // bf16 operand tile written by the row threads
   static constexpr int NUM_E = (MODE == BWD_DKDV) ? 2 : 1;
-  static constexpr int NS = 3;                 // streamed-tile ring depth
+  static constexpr int NS = 3;                 // streamed-tile ring depth (2 stages measured 7% slower)
   static constexpr int OFF_R0 = 0;
   static constexpr int OFF_R1 = OFF_R0 + R_BYTES;
   static constexpr int OFF_Y = OFF_R1 + R_BYTES;           // [NS stages][2 tiles]

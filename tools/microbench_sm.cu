@@ -11,12 +11,6 @@ using namespace vmae;
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void up2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 // 2^x for a pair, on the FMA pipe: round-to-nearest split + degree-3 minimax polynomial (rel. err 7.5e-5), exponent by integer add
 __device__ __forceinline__ unsigned long long exp2_poly2(unsigned long long x2) {
   float lo, hi; up2(x2, lo, hi);
@@ -128,7 +122,7 @@ __global__ void __launch_bounds__(128, 2) bench_kernel(long long* cycles, float*
           }
         }
         acc = (s0 + s1) * 1e-3f + __uint_as_float(u & 0x0fffffffu);
-      } else if (MODE == 10 || MODE == 11) {   // the forward's whole row phase: 4 loads, max, 128 exps (+sum, pack), 4 stores
+      } else if (MODE == 10 || MODE == 11 || MODE == 12) {   // the forward's whole row phase: 4 loads, max, 128 exps (+sum, pack), 4 stores
         uint32_t sc[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_off + c * 32, sc[c]);
@@ -147,10 +141,14 @@ __global__ void __launch_bounds__(128, 2) bench_kernel(long long* cycles, float*
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float p0 = fmaf(__uint_as_float(sc[c][i]), 1e-9f, -msl), p1 = fmaf(__uint_as_float(sc[c][i + 1]), 1e-9f, -msl);
-            if (MODE == 10) { p0 = ex2a(p0); p1 = ex2a(p1); } else { p0 = p0 * 0.001f + 0.5f; p1 = p1 * 0.001f + 0.5f; }
+            if (MODE != 11) { p0 = ex2a(p0); p1 = ex2a(p1); } else { p0 = p0 * 0.001f + 0.5f; p1 = p1 * 0.001f + 0.5f; }
             l4[c] += p0 + p1;
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-            sc[c][i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            if (MODE == 12) {
+              sc[c][i >> 1] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);   // truncating bf16x2 pack on the ALU pipe
+            } else {
+              __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+              sc[c][i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            }
           }
         }
         acc = ((l4[0] + l4[1]) + (l4[2] + l4[3])) * 1e-4f;
@@ -251,7 +249,7 @@ void run(const char* name, int ctas_per_sm, int active_warps, double unit_per_it
 int main(int argc, char** argv) {
   if (argc > 1) {   // MUFU / softmax-like scaling with the number of resident warps per SM sub-partition
     for (int c = 1; c <= 2; ++c) {
-      run<10>("fwd row phase", c, 4, 1); run<11>("fwd row phase, no MUFU", c, 4, 1);
+      run<10>("fwd row phase", c, 4, 1); run<11>("fwd row phase, no MUFU", c, 4, 1); run<12>("fwd row phase, PRMT pack", c, 4, 1);
       run<20>("row phase f32x2 poly 0/16", c, 4, 1); run<23>("row phase f32x2 poly 3/16", c, 4, 1); run<24>("row phase f32x2 poly 4/16", c, 4, 1);
       run<25>("row phase f32x2 poly 5/16", c, 4, 1); run<26>("row phase f32x2 poly 6/16", c, 4, 1); run<28>("row phase f32x2 poly 8/16", c, 4, 1);
     }
