@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VMAE_ABI_VERSION 1
+#define VMAE_ABI_VERSION 2
 
 #define VMAE_ERR_BAD_ARG (-1)
 #define VMAE_ERR_UNSUPPORTED (-2)
@@ -62,16 +62,31 @@ int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, lon
 int vmae_linear_wgrad(const void* dy, long long ld_dy, const void* x, long long ld_x, long long tokens, int n_out,
                       int k_in, float* dw, long long ld_dw, float* dbias, int k_splits, void* stream);
 
-/* ---- K2: flash attention on tcgen05/TMEM (non-causal, no mask, no dropout) --------------------------------------
+/* ---- K2: flash attention on tcgen05/TMEM (non-causal, no mask; optional attention-probability dropout) -----------
  * qkv: bf16 [B, L, 3, H, hd] (the packed projection output: q|k|v blocks, then head, then dim) — the layout of
  * Attention.qkv (tiny_vit.py:93,100) and of nn.MultiheadAttention.in_proj (mae_vit_adapter.py:40-48).
  * out: bf16 [B, L, H*hd]; lse: fp32 [B, H, L] (natural-log sum-exp of the scaled scores, saved for backward).
  * Replaces F.scaled_dot_product_attention (tiny_vit.py:103) and the MHA core of nn.TransformerEncoderLayer.
+ * p_drop > 0 drops attention probabilities in the kernel (nn.MultiheadAttention(dropout=p) inside the decoder layers,
+ * mae_vit_adapter.py:40-47): element (b, h, q, k) is kept with probability 1 - round(p*65536)/65536 according to a
+ * stateless hash of (seed, b, h, q, k); kept probabilities are scaled by 1/(1-p), the softmax normaliser is not. The
+ * backward call must receive the same (p_drop, seed). Statistical — not bit-wise — equivalence with torch's Philox stream.
  */
-int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream);
+int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, float p_drop,
+                  unsigned long long seed, void* stream);
 /* dqkv: bf16 [B, L, 3, H, hd]; delta: fp32 workspace [B, H, L] (rowsum(dO*O), written by the call). */
 int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
-                  int B, int L, int H, int hd, float scale, void* stream);
+                  int B, int L, int H, int hd, float scale, float p_drop, unsigned long long seed, void* stream);
+/* The keep mask the two calls above use, materialised as uint8 [B, H, L, L] (1 = kept). Test/debug helper. */
+int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_drop, unsigned long long seed, void* stream);
+
+/* ---- element dropout (nn.Dropout inside nn.TransformerEncoderLayer: dropout / dropout1 / dropout2, mae_vit_adapter.py:40-47)
+ * dst[i] = (add ? add[i] : 0) + keep(seed, i) * src[i] / (1 - p).  src: bf16 or fp32 (src_dtype); add: optional fp32 (the
+ * residual stream); dst: bf16 or fp32 (dst_dtype), may alias src. The same (p_drop, seed) reproduces the same mask, which is
+ * how backward re-applies it. vmae_dropout_mask writes the keep mask as uint8 [n] (test/debug helper). */
+int vmae_dropout_apply(const void* src, int src_dtype, const float* add, void* dst, int dst_dtype, long long n, float p_drop,
+                       unsigned long long seed, void* stream);
+int vmae_dropout_mask(void* mask, long long n, float p_drop, unsigned long long seed, void* stream);
 
 /* ---- K3: LayerNorm (nn.LayerNorm eps=1e-5: tiny_vit.py:112,115; decoder norms mae_vit_adapter.py:40-50) ---------
  * x: [rows, cols] fp32 or bf16 (x_dtype); y: bf16 or fp32 (y_dtype); mean/rstd: fp32 [rows] saved for backward. */

@@ -48,6 +48,22 @@ __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2; exp2
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Attention-probability dropout (nn.MultiheadAttention(dropout=p), mae_vit_adapter.py:40-47): a stateless hash of
+// (seed, batch*head, query, key pair) gives two 16-bit uniforms, so the forward and both backward kernels regenerate the same
+// keep mask without storing it. Element (q, k) is dropped when its half of the word is below thr = round(p * 65536).
+struct AttnDrop {
+  uint32_t seed_lo, seed_hi, thr;
+  float rp;   // 1 / (1 - thr / 65536)
+};
+__device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+constexpr uint32_t DROP_CQ = 0x9E3779B1u, DROP_CK = 0x85EBCA77u;
+// word for query row id `rid` (= (b*H + h)*L + q) and key pair kp (= k >> 1): low half -> even k, high half -> odd k
+__device__ __forceinline__ uint32_t drop_word(const AttnDrop& d, uint32_t rid, uint32_t kp) {
+  return drop_mix32(rid * DROP_CQ + kp * DROP_CK + d.seed_lo) ^ d.seed_hi;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -102,10 +118,10 @@ struct FwdCfg {
   static_assert(TMEM_NEED <= 256, "two CTAs per SM share the 512 TMEM columns");
 };
 
-template <int HD, int BKV>
+template <int HD, int BKV, bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale, const AttnDrop drop) {
   using Cfg = FwdCfg<HD, BKV>;
   static_assert(BKV == 128, "the row threads hold one 128-column score row in registers");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -207,6 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float sl2 = scale * LOG2E;
+    const uint32_t drop_base = (static_cast<uint32_t>((b * H + h) * L + q0 + row)) * DROP_CQ + drop.seed_lo;
     // Online softmax with a lazily updated reference maximum: O accumulates in TMEM across all KV blocks and is only
     // rescaled (TMEM -> registers -> TMEM) when some row of the warp sees its maximum grow by more than 2^8; otherwise the
     // stale reference is kept (P <= 256 stays exact enough in bf16 and l / O carry the same factor, which cancels).
@@ -274,9 +291,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // packed in place (slot i/2 has already been consumed when pair i is written): no second register array
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sc[c][i]), sl2, -msl));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sc[c][i + 1]), sl2, -msl));
-          l4[c] += p0 + p1;
+          float p0 = ex2_approx(fmaf(__uint_as_float(sc[c][i]), sl2, -msl));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sc[c][i + 1]), sl2, -msl));
+          l4[c] += p0 + p1;   // the normaliser sums the un-dropped probabilities
+          if (DROP) {
+            const uint32_t w = drop_mix32(drop_base + static_cast<uint32_t>((j * BKV + c * 32 + i) >> 1) * DROP_CK) ^ drop.seed_hi;
+            if ((w & 0xffffu) < drop.thr) p0 = 0.f;
+            if ((w >> 16) < drop.thr) p1 = 0.f;
+          }
           sc[c][i >> 1] = pack_bf16x2(p0, p1);
         }
       }
@@ -299,7 +321,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
+    const float inv_l = (DROP ? drop.rp : 1.0f) / l;
     const int q_row = q0 + row;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
@@ -384,12 +406,12 @@ struct BwdCfg {
 // 256 threads: warpgroup 0 = control (warp 0 UMMA issuer, warp 1 TMA producer), warpgroup 1 = one thread per row. As in the
 // forward, the row threads pull both score-like tiles of an iteration into registers with back-to-back TMEM loads and
 // hand the TMEM columns straight back, so T(it+1) is computed underneath the element-wise phase of iteration it.
-template <int HD, int BS, int MODE>
+template <int HD, int BS, int MODE, bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_constant__ CUtensorMap map_str_qkv,
                 const __grid_constant__ CUtensorMap map_res_do, const __grid_constant__ CUtensorMap map_str_do,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int H,
-                float scale) {
+                float scale, const AttnDrop drop) {
   using Cfg = BwdCfg<HD, BS, MODE>;
   static_assert(BS == 64, "the row threads hold two 64-column tiles in registers");
   constexpr int NS = Cfg::NS;
@@ -518,6 +540,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
     const float sl2 = scale * LOG2E;
     const int g_row = r0 + row;
     const long long stat_base = (static_cast<long long>(b) * H + h) * L;
+    // dropout hash base: DQ threads own a query row (keys vary), dK/dV threads own a key (query rows vary)
+    const uint32_t drop_base = (MODE == BWD_DQ) ? static_cast<uint32_t>((b * H + h) * L + g_row) * DROP_CQ + drop.seed_lo
+                                                : static_cast<uint32_t>(g_row >> 1) * DROP_CK + drop.seed_lo;
     float lse_row = 0.f, delta_row = 0.f;
     if (MODE == BWD_DQ && g_row < L) {
       lse_row = lse[stat_base + g_row] * LOG2E;
@@ -562,7 +587,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
           for (int i = 0; i < 32; ++i) {
             float p = ex2_approx(fmaf(__uint_as_float(ts[c][i]), sl2, -lse_row));
             if (valid < BS && c * 32 + i >= valid) p = 0.f;
-            tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - delta_row));
+            float dp = __uint_as_float(tp[c][i]);
+            if (DROP) {   // d(prob) = keep ? d(dropped prob) / (1 - p) : 0
+              const int col = it * BS + c * 32 + i;
+              const uint32_t w = drop_mix32(drop_base + static_cast<uint32_t>(col >> 1) * DROP_CK) ^ drop.seed_hi;
+              dp = (((col & 1) ? (w >> 16) : (w & 0xffffu)) < drop.thr) ? 0.f : dp * drop.rp;
+            }
+            tp[c][i] = __float_as_uint(p * (dp - delta_row));
           }
       } else {
         named_bar_sync(1, 128);   // the statistics deposited at the end of the previous iteration are visible
@@ -580,8 +611,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
             for (int t = 0; t < 4; ++t) {
               const int i = 4 * i4 + t;
               const float p = ex2_approx(fmaf(__uint_as_float(ts[c][i]), sl2, -lv[t]));
-              ts[c][i] = __float_as_uint(p);
-              tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - dv[t]));
+              float dp = __uint_as_float(tp[c][i]);
+              float pd = p;   // the dropped probability (scaled by 1/(1-p) when dV is written out)
+              if (DROP) {
+                const uint32_t rid = static_cast<uint32_t>((b * H + h) * L + it * BS + c * 32 + i);   // query row of this column
+                const uint32_t w = drop_mix32(rid * DROP_CQ + drop_base) ^ drop.seed_hi;
+                const bool dropped = (((g_row & 1) ? (w >> 16) : (w & 0xffffu)) < drop.thr);
+                dp = dropped ? 0.f : dp * drop.rp;
+                pd = dropped ? 0.f : p;
+              }
+              ts[c][i] = __float_as_uint(pd);
+              tp[c][i] = __float_as_uint(p * (dp - dv[t]));
             }
           }
         named_bar_sync(1, 128);   // everybody has read this block's statistics
@@ -620,7 +660,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
           for (int i = 0; i < 32; i += 8) {
             uint4 pk;
             // dS was accumulated without the softmax scale; ACC1 of the dK/dV mode is dV = P^T dO (no scale)
-            const float f = (MODE == BWD_DKDV && a == 1) ? 1.0f : scale;
+            const float f = (MODE == BWD_DKDV && a == 1) ? (DROP ? drop.rp : 1.0f) : scale;
             pk.x = pack_bf16x2(__uint_as_float(r[i]) * f, __uint_as_float(r[i + 1]) * f);
             pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * f, __uint_as_float(r[i + 3]) * f);
             pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * f, __uint_as_float(r[i + 5]) * f);
@@ -643,25 +683,42 @@ static int make_map_rows(CUtensorMap* m, const void* base, int B, int L, int wid
   return make_tmap_bf16(m, base, 3, dims, str, box, hd * 2);
 }
 
+static AttnDrop make_drop(float p_drop, unsigned long long seed) {
+  AttnDrop d;
+  d.seed_lo = static_cast<uint32_t>(seed);
+  d.seed_hi = static_cast<uint32_t>(seed >> 32);
+  d.thr = static_cast<uint32_t>(p_drop * 65536.0f + 0.5f);
+  d.rp = 65536.0f / (65536.0f - static_cast<float>(d.thr));
+  return d;
+}
+
 template <int HD, int BKV>
-static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t stream) {
+static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, float p_drop, unsigned long long seed,
+                      cudaStream_t stream) {
   using Cfg = FwdCfg<HD, BKV>;
   CUtensorMap mq, mkv;
   int rc = make_map_rows(&mq, qkv, B, L, 3 * H * HD, HD, 128);
   if (rc) return rc;
   rc = make_map_rows(&mkv, qkv, B, L, 3 * H * HD, HD, BKV);
   if (rc) return rc;
-  auto kern = attn_fwd_kernel<HD, BKV>;
-  VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const AttnDrop drop = make_drop(p_drop, seed);
   dim3 grid((L + 127) / 128, H, B);
-  kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale);
+  if (drop.thr > 0) {
+    auto kern = attn_fwd_kernel<HD, BKV, true>;
+    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop);
+  } else {
+    auto kern = attn_fwd_kernel<HD, BKV, false>;
+    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop);
+  }
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
 
 template <int HD, int BS, int MODE>
 static int launch_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int L, int H,
-                      float scale, cudaStream_t stream) {
+                      float scale, float p_drop, unsigned long long seed, cudaStream_t stream) {
   using Cfg = BwdCfg<HD, BS, MODE>;
   CUtensorMap m_res_qkv, m_str_qkv, m_res_do, m_str_do;
   int rc = make_map_rows(&m_res_qkv, qkv, B, L, 3 * H * HD, HD, 128);
@@ -672,12 +729,33 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
   if (rc) return rc;
   rc = make_map_rows(&m_str_do, dout, B, L, H * HD, HD, BS);
   if (rc) return rc;
-  auto kern = attn_bwd_kernel<HD, BS, MODE>;
-  VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const AttnDrop drop = make_drop(p_drop, seed);
   dim3 grid((L + 127) / 128, H, B);
-  kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H, scale);
+  if (drop.thr > 0) {
+    auto kern = attn_bwd_kernel<HD, BS, MODE, true>;
+    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H,
+                                                             scale, drop);
+  } else {
+    auto kern = attn_bwd_kernel<HD, BS, MODE, false>;
+    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H,
+                                                             scale, drop);
+  }
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
+}
+
+// keep mask of the attention-probability dropout, materialised for tests: mask[b, h, q, k] = 1 (kept) / 0 (dropped)
+__global__ void __launch_bounds__(256) attn_dropout_mask_kernel(uint8_t* __restrict__ mask, long long rows, int L, const AttnDrop drop) {
+  const long long total = rows * ((L + 1) / 2);
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += gridDim.x * 256LL) {
+    const long long rid = idx / ((L + 1) / 2);
+    const int kp = static_cast<int>(idx % ((L + 1) / 2));
+    const uint32_t w = drop_word(drop, static_cast<uint32_t>(rid), static_cast<uint32_t>(kp));
+    mask[rid * L + 2 * kp] = (w & 0xffffu) >= drop.thr;
+    if (2 * kp + 1 < L) mask[rid * L + 2 * kp + 1] = (w >> 16) >= drop.thr;
+  }
 }
 
 }  // namespace vmae
@@ -694,19 +772,33 @@ extern "C" int vmae_att_trace_select(int bx, int by, int bz, int mode) {
 extern "C" int vmae_att_trace_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_att_trace, sizeof(long long) * 2 * 32 * 8); }
 #endif
 
-extern "C" int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream) {
+extern "C" int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, float p_drop,
+                             unsigned long long seed, void* stream) {
   VMAE_CHECK_ARG(qkv && out && lse, "vmae_attn_fwd: null pointer");
   VMAE_CHECK_ARG(B > 0 && L > 0 && H > 0, "vmae_attn_fwd: bad shape B=%d L=%d H=%d", B, L, H);
   VMAE_CHECK_ARG(B <= 65535 && H <= 65535, "vmae_attn_fwd: B and H must be <= 65535");
+  VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_attn_fwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  VMAE_CHECK_ARG((long long)B * H * L < (1LL << 32), "vmae_attn_fwd: B*H*L must fit 32 bits");
   cudaStream_t s = (cudaStream_t)stream;
-  if (hd == 64) return launch_fwd<64, 128>(qkv, out, lse, B, L, H, scale, s);
-  if (hd == 32) return launch_fwd<32, 128>(qkv, out, lse, B, L, H, scale, s);
+  if (hd == 64) return launch_fwd<64, 128>(qkv, out, lse, B, L, H, scale, p_drop, seed, s);
+  if (hd == 32) return launch_fwd<32, 128>(qkv, out, lse, B, L, H, scale, p_drop, seed, s);
   return fail(VMAE_ERR_UNSUPPORTED, "vmae_attn_fwd: head_dim %d unsupported (32 or 64)", hd);
 }
 
+extern "C" int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_drop, unsigned long long seed, void* stream) {
+  VMAE_CHECK_ARG(mask && B > 0 && L > 0 && H > 0, "vmae_attn_dropout_mask: bad args");
+  VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_attn_dropout_mask: p_drop=%f outside [0, 1)", (double)p_drop);
+  VMAE_CHECK_ARG((long long)B * H * L < (1LL << 32), "vmae_attn_dropout_mask: B*H*L must fit 32 bits");
+  attn_dropout_mask_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>((uint8_t*)mask, (long long)B * H * L, L, make_drop(p_drop, seed));
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
 extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
-                             int L, int H, int hd, float scale, void* stream) {
+                             int L, int H, int hd, float scale, float p_drop, unsigned long long seed, void* stream) {
   VMAE_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vmae_attn_bwd: null pointer");
+  VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_attn_bwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  VMAE_CHECK_ARG((long long)B * H * L < (1LL << 32), "vmae_attn_bwd: B*H*L must fit 32 bits");
   VMAE_CHECK_ARG(B > 0 && L > 0 && H > 0, "vmae_attn_bwd: bad shape B=%d L=%d H=%d", B, L, H);
   VMAE_CHECK_ARG(B <= 65535 && H <= 65535, "vmae_attn_bwd: B and H must be <= 65535");
   cudaStream_t s = (cudaStream_t)stream;
@@ -717,16 +809,16 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
   if (hd == 64) {
     attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
     VMAE_LAUNCH_CHECK();
-    rc = launch_bwd<64, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    rc = launch_bwd<64, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
     if (rc) return rc;
-    return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
   }
   if (hd == 32) {
     attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
     VMAE_LAUNCH_CHECK();
-    rc = launch_bwd<32, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    rc = launch_bwd<32, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
     if (rc) return rc;
-    return launch_bwd<32, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, s);
+    return launch_bwd<32, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
   }
   return fail(VMAE_ERR_UNSUPPORTED, "vmae_attn_bwd: head_dim %d unsupported (32 or 64)", hd);
 }

@@ -243,6 +243,45 @@ __global__ void __launch_bounds__(EW_THREADS, (NV <= 4) ? 2 : 1) layernorm_bwd_k
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Element dropout with a stateless keep mask: one 32-bit hash per element pair, 16 bits per element.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ew_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// keep bits of elements 2*pair (low half) and 2*pair+1 (high half)
+__device__ __forceinline__ uint32_t ew_drop_word(unsigned long long seed, long long pair) {
+  const uint32_t hi = ew_mix32(static_cast<uint32_t>(static_cast<unsigned long long>(pair) >> 32) ^ static_cast<uint32_t>(seed >> 32));
+  return ew_mix32(static_cast<uint32_t>(pair) * 0x9E3779B1u + static_cast<uint32_t>(seed) + hi);
+}
+template <typename ST, typename DT>
+__global__ void __launch_bounds__(EW_THREADS) dropout_apply_kernel(const ST* __restrict__ src, const float* __restrict__ add, DT* __restrict__ dst,
+                                                                    long long n, uint32_t thr, float rp, unsigned long long seed) {
+  const long long n4 = n / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = load4<ST>(src + 4 * i);
+    const uint32_t w0 = ew_drop_word(seed, 2 * i), w1 = ew_drop_word(seed, 2 * i + 1);
+    v.x = ((w0 & 0xffffu) < thr) ? 0.f : v.x * rp;
+    v.y = ((w0 >> 16) < thr) ? 0.f : v.y * rp;
+    v.z = ((w1 & 0xffffu) < thr) ? 0.f : v.z * rp;
+    v.w = ((w1 >> 16) < thr) ? 0.f : v.w * rp;
+    if (add) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(add) + i);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    store4<DT>(dst + 4 * i, v);
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS) dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, uint32_t thr, unsigned long long seed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t w = ew_drop_word(seed, i >> 1);
+    mask[i] = (((i & 1) ? (w >> 16) : (w & 0xffffu)) >= thr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // casts / scale
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
@@ -472,6 +511,38 @@ extern "C" int vmae_layernorm_bwd(const void* dy, int dy_dtype, const void* x, i
   if (dy_dtype == VMAE_DTYPE_BF16 && x_dtype == VMAE_DTYPE_BF16) return ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx_resid, dx_out, dx_out_bf16, dgamma, dbeta, rows, cols, s);
   if (dy_dtype == VMAE_DTYPE_F32 && x_dtype == VMAE_DTYPE_BF16) return ln_bwd_dispatch<float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx_resid, dx_out, dx_out_bf16, dgamma, dbeta, rows, cols, s);
   return fail(VMAE_ERR_BAD_ARG, "vmae_layernorm_bwd: bad dtypes %d/%d", dy_dtype, x_dtype);
+}
+
+template <typename ST>
+static int dropout_dispatch(const void* src, const float* add, void* dst, int dst_dtype, long long n, uint32_t thr, float rp,
+                            unsigned long long seed, cudaStream_t s) {
+  const int grid = ew_grid(n / 4, EW_THREADS);
+  if (dst_dtype == VMAE_DTYPE_BF16)
+    dropout_apply_kernel<ST, __nv_bfloat16><<<grid, EW_THREADS, 0, s>>>((const ST*)src, add, (__nv_bfloat16*)dst, n, thr, rp, seed);
+  else
+    dropout_apply_kernel<ST, float><<<grid, EW_THREADS, 0, s>>>((const ST*)src, add, (float*)dst, n, thr, rp, seed);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+extern "C" int vmae_dropout_apply(const void* src, int src_dtype, const float* add, void* dst, int dst_dtype, long long n, float p_drop,
+                                  unsigned long long seed, void* stream) {
+  VMAE_CHECK_ARG(n >= 0 && n % 4 == 0 && (n == 0 || (src && dst)), "vmae_dropout_apply: bad args (n must be a multiple of 4)");
+  VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_dropout_apply: p_drop=%f outside [0, 1)", (double)p_drop);
+  VMAE_CHECK_ARG((src_dtype == VMAE_DTYPE_BF16 || src_dtype == VMAE_DTYPE_F32) && (dst_dtype == VMAE_DTYPE_BF16 || dst_dtype == VMAE_DTYPE_F32),
+                 "vmae_dropout_apply: bad dtypes %d/%d", src_dtype, dst_dtype);
+  if (n == 0) return VMAE_OK;
+  const uint32_t thr = static_cast<uint32_t>(p_drop * 65536.0f + 0.5f);
+  const float rp = 65536.0f / (65536.0f - static_cast<float>(thr));
+  if (src_dtype == VMAE_DTYPE_BF16) return dropout_dispatch<__nv_bfloat16>(src, add, dst, dst_dtype, n, thr, rp, seed, (cudaStream_t)stream);
+  return dropout_dispatch<float>(src, add, dst, dst_dtype, n, thr, rp, seed, (cudaStream_t)stream);
+}
+extern "C" int vmae_dropout_mask(void* mask, long long n, float p_drop, unsigned long long seed, void* stream) {
+  VMAE_CHECK_ARG(n >= 0 && (n == 0 || mask), "vmae_dropout_mask: bad args");
+  VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_dropout_mask: p_drop=%f outside [0, 1)", (double)p_drop);
+  if (n == 0) return VMAE_OK;
+  dropout_mask_kernel<<<ew_grid(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>((uint8_t*)mask, n, static_cast<uint32_t>(p_drop * 65536.0f + 0.5f), seed);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
 }
 
 extern "C" int vmae_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {

@@ -49,16 +49,16 @@ class DecoderLayer(nn.Module):
         self.dropout2 = nn.Dropout(dropout)
         self.nhead = nhead
 
-    def forward(self, x):
-        """x: fp32 [B, N, D] -> fp32 [B, N, D]"""
-        if self.training and self.dropout.p > 0.0:
-            raise NotImplementedError(
-                "decoder dropout > 0 in training mode needs in-kernel attention-probability dropout, which the sm_100a "
-                "flash kernel does not implement yet; set config['model']['decoder_dropout'] = 0.0 (parity runs do)")
+    def forward(self, x, seeds=None):
+        """x: fp32 [B, N, D] -> fp32 [B, N, D]. In training mode with dropout p > 0 the four dropout sites of the reference
+        layer are active (attention probabilities in the flash kernel, dropout1, dropout after GELU, dropout2); the masks come
+        from a stateless hash seeded from torch's CPU generator, so runs are reproducible under torch.manual_seed but the
+        realisations differ from PyTorch's Philox stream (statistical, not bit-wise, equivalence)."""
         B, N, D = x.shape
         a = self.self_attn
+        p = float(self.dropout.p) if self.training else 0.0
         y = ops.transformer_block(x.reshape(B * N, D), self.norm1, a.in_proj_weight, a.in_proj_bias, a.out_proj, self.norm2,
-                                  self.linear1, self.linear2, self.nhead, B, N)
+                                  self.linear1, self.linear2, self.nhead, B, N, p_drop=p, seeds=seeds)
         return y.view(B, N, D)
 
 

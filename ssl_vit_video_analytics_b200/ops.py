@@ -270,22 +270,59 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_resid=None, dgamma=None, dbeta
     return dx, dx_b, dgamma, dbeta
 
 
-def attn_fwd(qkv, B, Lq, H, hd):
+def attn_fwd(qkv, B, Lq, H, hd, p_drop=0.0, seed=0):
     out = torch.empty((B * Lq, H * hd), device=qkv.device, dtype=BF16)
     lse = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
     L.check(_run("attn_fwd", 4.0 * B * H * Lq * Lq * hd, lambda: L.load().vmae_attn_fwd(
-        _p(qkv), _p(out), _p(lse), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream())), "vmae_attn_fwd")
+        _p(qkv), _p(out), _p(lse), B, Lq, H, hd, 1.0 / math.sqrt(hd), float(p_drop), int(seed), _stream())), "vmae_attn_fwd")
     _count()
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd):
+def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, p_drop=0.0, seed=0):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
     L.check(_run("attn_bwd", 10.0 * B * H * Lq * Lq * hd, lambda: L.load().vmae_attn_bwd(
-        _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), _stream())), "vmae_attn_bwd")
+        _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), float(p_drop), int(seed),
+        _stream())), "vmae_attn_bwd")
     _count(3)
     return dqkv
+
+
+def attn_dropout_mask(B, Lq, H, p_drop, seed, device):
+    """uint8 [B, H, L, L] keep mask of the in-kernel attention-probability dropout (test helper)."""
+    mask = torch.empty((B, H, Lq, Lq), device=device, dtype=torch.uint8)
+    L.check(L.load().vmae_attn_dropout_mask(_p(mask), B, Lq, H, float(p_drop), int(seed), _stream()), "vmae_attn_dropout_mask")
+    return mask
+
+
+def dropout_apply(src, p_drop, seed, *, add=None, out_dtype=None, out=None):
+    """out = (add or 0) + keep(seed, i) * src / (1 - p): nn.Dropout with a stateless, reproducible mask (same seed -> same mask,
+    which is how backward re-applies it). src bf16/fp32; add fp32 residual (optional); out bf16/fp32, may be src itself."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.numel() % 4 == 0
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=out_dtype or src.dtype)
+    if add is not None:
+        assert add.dtype == F32 and add.is_contiguous() and add.numel() == src.numel()
+    n = src.numel()
+    nbytes = float(n) * (src.element_size() + out.element_size() + (4 if add is not None else 0))
+    L.check(_run("dropout", nbytes, lambda: L.load().vmae_dropout_apply(_p(src), _dt(src), _p(add), _p(out), _dt(out), n, float(p_drop), int(seed),
+                                                                       _stream())), "vmae_dropout_apply")
+    _count()
+    return out
+
+
+def dropout_mask(n, p_drop, seed, device):
+    """uint8 [n] keep mask dropout_apply uses for (p_drop, seed) (test helper)."""
+    mask = torch.empty((n,), device=device, dtype=torch.uint8)
+    L.check(L.load().vmae_dropout_mask(_p(mask), n, float(p_drop), int(seed), _stream()), "vmae_dropout_mask")
+    return mask
+
+
+def new_dropout_seeds(k):
+    """k fresh 63-bit seeds from torch's CPU generator (deterministic under torch.manual_seed, no device sync)."""
+    return [int(v) for v in torch.randint(0, 2 ** 62, (k,), dtype=torch.int64).tolist()]
 
 
 # ======================================================================================================================
@@ -483,7 +520,8 @@ class TransformerBlockFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, B, Lq):
+    def forward(ctx, x, ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, B, Lq,
+                p_drop=0.0, seeds=None):
         _need_cuda(x)
         D = x.shape[-1]
         assert x.dtype == F32 and x.is_contiguous() and x.shape[0] == B * Lq
@@ -493,17 +531,29 @@ class TransformerBlockFn(torch.autograd.Function):
         ln1_w, ln1_b, ln2_w, ln2_b = f(ln1_w), f(ln1_b), f(ln2_w), f(ln2_b)
         qkv_b, proj_b, fc1_b, fc2_b = f(qkv_b), f(proj_b), f(fc1_b), f(fc2_b)
         wq, wp, w1, w2 = cast_weight(qkv_w), cast_weight(proj_w), cast_weight(fc1_w), cast_weight(fc2_w)
+        drop = p_drop > 0.0
+        if drop:   # nn.TransformerEncoderLayer's four dropout sites: attention probabilities, dropout1, dropout (after GELU), dropout2
+            s_attn, s_d1, s_act, s_d2 = seeds
         ln1, mean1, rstd1 = layernorm_fwd(x, ln1_w, ln1_b)
         qkv = linear_fwd(ln1, wq, qkv_b)
-        o, lse = attn_fwd(qkv, B, Lq, num_heads, hd)
-        x1 = linear_fwd(o, wp, proj_b, residual=x)
+        o, lse = attn_fwd(qkv, B, Lq, num_heads, hd, p_drop, s_attn if drop else 0)
+        if drop:
+            x1 = dropout_apply(linear_fwd(o, wp, proj_b), p_drop, s_d1, add=x, out_dtype=F32)
+        else:
+            x1 = linear_fwd(o, wp, proj_b, residual=x)
         ln2, mean2, rstd2 = layernorm_fwd(x1, ln2_w, ln2_b)
         h_pre = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
         act = linear_fwd(ln2, w1, fc1_b, act=L.ACT_GELU, aux_out=h_pre)
-        x2 = linear_fwd(act, w2, fc2_b, residual=x1)
+        if drop:   # same mask on the activation and on the saved gelu' (so backward needs no extra pass)
+            dropout_apply(act, p_drop, s_act, out=act)
+            dropout_apply(h_pre, p_drop, s_act, out=h_pre)
+            x2 = dropout_apply(linear_fwd(act, w2, fc2_b), p_drop, s_d2, add=x1, out_dtype=F32)
+        else:
+            x2 = linear_fwd(act, w2, fc2_b, residual=x1)
         ctx.save_for_backward(x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2)
         ctx.dims = (B, Lq, num_heads, hd)
         ctx.params = params
+        ctx.drop = (p_drop, tuple(seeds)) if drop else None
         return x2
 
     @staticmethod
@@ -511,9 +561,13 @@ class TransformerBlockFn(torch.autograd.Function):
         (x, ln1_w, mean1, rstd1, ln1, qkv, o, lse, x1, ln2_w, mean2, rstd2, ln2, h_pre, act, wq, wp, w1, w2) = ctx.saved_tensors
         B, Lq, H, hd = ctx.dims
         dx2 = dx2.contiguous()
+        p_drop, (s_attn, s_d1, s_act, s_d2) = ctx.drop if ctx.drop is not None else (0.0, (0, 0, 0, 0))
         # the LayerNorm backward of the block that produced dx2 already wrote a bf16 copy of it (same kernel, no extra read)
         sh = _GRAD_SHADOW[0]
-        dx2_b = sh[2] if (sh is not None and sh[0] == dx2._cdata) else cast_bf16(dx2)
+        if p_drop > 0.0:
+            dx2_b = dropout_apply(dx2, p_drop, s_d2, out_dtype=BF16)      # gradient entering fc2 = dropout2 mask * dx2 / (1-p)
+        else:
+            dx2_b = sh[2] if (sh is not None and sh[0] == dx2._cdata) else cast_bf16(dx2)
         _GRAD_SHADOW[0] = None
         P = ctx.params  # ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b
         tgt = [(_direct_grad(p) if ctx.needs_input_grad[i + 1] else None) for i, p in enumerate(P)]
@@ -525,9 +579,11 @@ class TransformerBlockFn(torch.autograd.Function):
         dw1, db1 = linear_wgrad_bias(dh, ln2, t_w1, t_bb1)
         dx1, dx1_b, dg2, dbeta2 = layernorm_bwd(dln2, x1, ln2_w, mean2, rstd2, dx_resid=dx2, dgamma=t_g2, dbeta=t_b2, want_bf16=True)
         # ---- attention branch
+        if p_drop > 0.0:
+            dx1_b = dropout_apply(dx1, p_drop, s_d1, out_dtype=BF16)      # gradient entering out_proj = dropout1 mask * dx1 / (1-p)
         do = linear_dgrad(dx1_b, wp)
         dwp, dbp = linear_wgrad_bias(dx1_b, o, t_wp, t_bp)
-        dqkv = attn_bwd(qkv, o, do, lse, B, Lq, H, hd)
+        dqkv = attn_bwd(qkv, o, do, lse, B, Lq, H, hd, p_drop, s_attn)
         dln1 = linear_dgrad(dqkv, wq)
         dwq, dbq = linear_wgrad_bias(dqkv, ln1, t_wq, t_bq)
         dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, dgamma=t_g1, dbeta=t_b1, want_bf16=True)
@@ -540,12 +596,15 @@ class TransformerBlockFn(torch.autograd.Function):
                 _grad_done(P[i])
         for i in range(12):
             out.append(None if tgt[i] is not None else grads[i])
-        return (dx, *out, None, None, None)
+        return (dx, *out, None, None, None, None, None)
 
 
-def transformer_block(x, ln1, qkv_w, qkv_b, proj, ln2, fc1, fc2, num_heads, B, Lq):
+def transformer_block(x, ln1, qkv_w, qkv_b, proj, ln2, fc1, fc2, num_heads, B, Lq, p_drop=0.0, seeds=None):
+    """p_drop > 0: dropout at the four sites of nn.TransformerEncoderLayer (training mode); seeds = 4 integers (new_dropout_seeds)."""
+    if p_drop > 0.0 and seeds is None:
+        seeds = new_dropout_seeds(4)
     return TransformerBlockFn.apply(x, ln1.weight, ln1.bias, qkv_w, qkv_b, proj.weight, proj.bias, ln2.weight, ln2.bias,
-                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias, num_heads, B, Lq)
+                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias, num_heads, B, Lq, float(p_drop), seeds)
 
 
 class LinearResidualF32Fn(torch.autograd.Function):

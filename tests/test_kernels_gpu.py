@@ -353,3 +353,93 @@ def test_im2col_col2im_and_image_im2col(env, stride):
     c2, ho, wo = ops.im2col3x3_image(img, stride, 32)
     u2 = F.unfold(img, 3, padding=1, stride=stride).permute(0, 2, 1).reshape(-1, 27)
     assert torch.equal(c2[:, :27].float(), u2.bfloat16().float()) and float(c2[:, 27:].abs().max()) == 0.0
+
+
+# ---- dropout (nn.TransformerEncoderLayer(dropout=0.1) of the reference decoder, mae_vit_adapter.py:40-47) -------------------
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_element_dropout_mask_statistics_and_apply(env, p):
+    ops, L, dev, g = env
+    n = 1 << 20
+    seed = 1234567
+    keep = ops.dropout_mask(n, p, seed, dev).bool()
+    assert abs(float(keep.float().mean()) - (1 - p)) < 3e-3                       # 1M Bernoulli draws: sigma ~ 5e-4
+    assert torch.equal(keep, ops.dropout_mask(n, p, seed, dev).bool())             # same seed -> same mask
+    assert float((keep ^ ops.dropout_mask(n, p, seed + 1, dev).bool()).float().mean()) > 0.1
+    pair = keep.view(-1, 2).float()                                                # the two halves of one hash word are independent
+    assert abs(float((pair[:, 0] * pair[:, 1]).mean()) - (1 - p) ** 2) < 3e-3
+    p_eff = round(p * 65536) / 65536
+    src = torch.randn(n, device=dev, generator=g)
+    add = torch.randn(n, device=dev, generator=g)
+    ref = add + keep.float() * src / (1 - p_eff)
+    assert relerr(ops.dropout_apply(src, p, seed, add=add, out_dtype=torch.float32), ref) < 1e-6
+    assert relerr(ops.dropout_apply(src.bfloat16(), p, seed, out_dtype=torch.bfloat16), keep.float() * src.bfloat16().float() / (1 - p_eff)) < 5e-3
+    assert torch.equal(ops.dropout_apply(src, 0.0, seed, out_dtype=torch.float32), src)
+
+
+@pytest.mark.parametrize("B,Lq,H,hd", [(1, 64, 1, 64), (2, 160, 3, 64), (1, 300, 2, 64), (2, 196, 4, 32)])
+def test_flash_attention_dropout_fwd_bwd(env, B, Lq, H, hd):
+    """The kernels regenerate the keep mask from (seed, b, h, q, k); with that mask materialised, a plain PyTorch attention with
+    explicit dropout must give the same output and the same q/k/v gradients."""
+    ops, L, dev, g = env
+    p, seed = 0.1, 987654321
+    p_eff = round(p * 65536) / 65536
+    qkv = torch.randn(B, Lq, 3, H, hd, device=dev, generator=g).bfloat16()
+    dout = torch.randn(B, Lq, H * hd, device=dev, generator=g).bfloat16()
+    keep = ops.attn_dropout_mask(B, Lq, H, p, seed, dev).float()                   # [B, H, L, L]
+    assert abs(float(keep.mean()) - (1 - p_eff)) < 0.01
+    out, lse = ops.attn_fwd(qkv.view(B * Lq, -1), B, Lq, H, hd, p, seed)
+    dqkv = ops.attn_bwd(qkv.view(B * Lq, -1), out, dout.view(B * Lq, -1), lse, B, Lq, H, hd, p, seed).view(B, Lq, 3, H, hd)
+    q32 = qkv.float().requires_grad_(True)
+    q, k, v = [q32[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    prob = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    ref = ((prob * keep / (1 - p_eff)) @ v).permute(0, 2, 1, 3).reshape(B, Lq, H * hd)
+    ref.backward(dout.float())
+    assert relerr(out.view(B, Lq, -1), ref) < BF16_TOL
+    for i, name in enumerate("qkv"):
+        assert relerr(dqkv[:, :, i], q32.grad[:, :, i]) < 2 * BF16_TOL, name
+    out0, _ = ops.attn_fwd(qkv.view(B * Lq, -1), B, Lq, H, hd)                      # p = 0 path untouched
+    assert relerr(out0.view(B, Lq, -1), (prob @ v).permute(0, 2, 1, 3).reshape(B, Lq, H * hd)) < BF16_TOL
+
+
+def test_transformer_block_with_dropout_matches_explicit_masks(env):
+    """One decoder layer with p = 0.1 at all four dropout sites vs fp32 PyTorch using the very masks the kernels generate."""
+    ops, L, dev, g = env
+    B, Lq, D, H, p = 2, 160, 384, 6, 0.1
+    hd = D // H
+    p_eff = round(p * 65536) / 65536
+    torch.manual_seed(0)
+    ln1, ln2 = torch.nn.LayerNorm(D).to(dev), torch.nn.LayerNorm(D).to(dev)
+    qkv, proj = torch.nn.Linear(D, 3 * D).to(dev), torch.nn.Linear(D, D).to(dev)
+    fc1, fc2 = torch.nn.Linear(D, 4 * D).to(dev), torch.nn.Linear(4 * D, D).to(dev)
+    mods = [ln1, qkv, proj, ln2, fc1, fc2]
+    x = torch.randn(B * Lq, D, device=dev, generator=g)
+    seeds = [11, 22, 33, 44]
+    xo = x.clone().requires_grad_(True)
+    y = ops.transformer_block(xo, ln1, qkv.weight, qkv.bias, proj, ln2, fc1, fc2, H, B, Lq, p_drop=p, seeds=seeds)
+    dy = torch.randn(B * Lq, D, device=dev, generator=g)
+    y.backward(dy)
+    got = {n_: p_.grad.clone() for m in mods for n_, p_ in [(f"{id(m)}.{k}", v) for k, v in m.named_parameters()]}
+    gx = xo.grad.clone()
+    for m in mods:
+        m.zero_grad()
+    # reference with explicit masks
+    s_attn, s_d1, s_act, s_d2 = seeds
+    k_attn = ops.attn_dropout_mask(B, Lq, H, p, s_attn, dev).float()
+    k_d1 = ops.dropout_mask(B * Lq * D, p, s_d1, dev).float().view(B * Lq, D)
+    k_act = ops.dropout_mask(B * Lq * 4 * D, p, s_act, dev).float().view(B * Lq, 4 * D)
+    k_d2 = ops.dropout_mask(B * Lq * D, p, s_d2, dev).float().view(B * Lq, D)
+    xr = x.clone().requires_grad_(True)
+    qkv_r = qkv(ln1(xr)).view(B, Lq, 3, H, hd)
+    q, k, v = [qkv_r[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    prob = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1) * k_attn / (1 - p_eff)
+    o = (prob @ v).permute(0, 2, 1, 3).reshape(B * Lq, D)
+    x1 = xr + proj(o) * k_d1 / (1 - p_eff)
+    x2 = x1 + fc2(F.gelu(fc1(ln2(x1))) * k_act / (1 - p_eff)) * k_d2 / (1 - p_eff)
+    x2.backward(dy)
+    assert relerr(y, x2) < BF16_TOL
+    assert relerr(gx, xr.grad) < 2 * BF16_TOL
+    for m in mods:
+        for kname, prm in m.named_parameters():
+            ref_g, our_g = prm.grad, got[f"{id(m)}.{kname}"]
+            cos = float((ref_g.flatten().double() @ our_g.flatten().double()) / (ref_g.norm().double() * our_g.norm().double() + 1e-300))
+            assert cos > 0.999, (type(m).__name__, kname, cos)

@@ -190,3 +190,44 @@ def test_second_backward_accumulates_directly_into_grad_buffers():
     for k, p in model.named_parameters():
         assert p.grad.data_ptr() == ptrs[k]
         assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-3, atol=1e-6 + 2e-3 * float(g1[k].abs().max())), k
+
+
+def test_decoder_dropout_default_config_trains_and_is_reproducible():
+    """The reference hard-wires nn.TransformerEncoderLayer's dropout 0.1 in the decoder (mae_vit_adapter.py:40-47). In training
+    mode our drop-in applies it at the same four sites; the realisation is seeded from torch's CPU generator (reproducible),
+    eval mode is dropout-free, and the expected loss stays close to the dropout-free loss."""
+    from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+
+    cfg = {"dataset": dict(TINY_CFG["dataset"]), "model": dict(TINY_CFG["model"])}
+    del cfg["model"]["decoder_dropout"]          # reference config has no such key -> 0.1 as in the reference
+    model = build_ours(cfg, seed=3).cuda().train()
+    assert model.decoder_blocks.layers[0].dropout.p == pytest.approx(0.1)
+    g = torch.Generator().manual_seed(5)
+    clip = torch.randn(2, 3, cfg["dataset"]["clip_len"], 32, 32, generator=g).cuda()
+    torch.manual_seed(7)
+    mask = get_tube_mask(2, cfg["dataset"]["clip_len"], 16, 0.75).cuda()
+
+    def run(seed):
+        torch.manual_seed(seed)
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = model(clip, mask)
+        loss = ops.masked_mse(pred, clip, mask, 1, 8, 1)
+        loss.backward()
+        gsum = sum(float(p.grad.double().abs().sum()) for p in model.parameters() if p.grad is not None)
+        return pred.detach().float(), float(loss), gsum
+
+    p1, l1, g1 = run(11)
+    p2, l2, g2 = run(11)
+    p3, l3, _ = run(12)
+    # same torch seed -> same masks -> the same step up to the summation order of the atomics (BatchNorm statistics, split-K)
+    same = float((p1 - p2).abs().max() / p1.abs().max())
+    other = float((p1 - p3).abs().max() / p1.abs().max())
+    assert same < 2e-2 and abs(l1 - l2) < 1e-3 * abs(l1), (same, l1, l2)
+    assert other > 5 * max(same, 1e-3), (same, other)                # another seed -> another realisation
+    assert all(map(lambda v: v == v and abs(v) != float("inf"), (l1, l3, g1))) and abs(l1 - l3) < 0.5
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        e1, e2 = model(clip, mask).float(), model(clip, mask).float()
+    assert torch.equal(e1, e2)                                       # eval: no dropout

@@ -47,7 +47,7 @@ def mode_fwd():
         scale = 1.0 / math.sqrt(hd)
         out = torch.full((B, Lq, H * hd), float("nan"), device=dev, dtype=torch.bfloat16)
         lse = torch.full((B, H, Lq), float("nan"), device=dev, dtype=torch.float32)
-        L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, stream()), "attn_fwd")
+        L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_fwd")
         torch.cuda.synchronize()
         ro, rl = ref_attn(qkv, scale)
         e1, e2 = rel(out, ro), (lse - rl).abs().max().item()
@@ -66,10 +66,10 @@ def mode_bwd():
         scale = 1.0 / math.sqrt(hd)
         out = torch.empty(B, Lq, H * hd, device=dev, dtype=torch.bfloat16)
         lse = torch.empty(B, H, Lq, device=dev, dtype=torch.float32)
-        L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, stream()), "attn_fwd")
+        L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_fwd")
         dqkv = torch.full_like(qkv, float("nan"))
         delta = torch.empty(B, H, Lq, device=dev, dtype=torch.float32)
-        L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, stream()), "attn_bwd")
+        L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_bwd")
         torch.cuda.synchronize()
         qf = qkv.float().requires_grad_(True)
         ro, _ = ref_attn(qf, scale)
@@ -105,8 +105,8 @@ def mode_perf():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / iters
 
-        tf = timeit(lambda: L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, stream()), "f"))
-        tb = timeit(lambda: L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, stream()), "b"))
+        tf = timeit(lambda: L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, 0.0, 0, stream()), "f"))
+        tb = timeit(lambda: L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "b"))
         q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
         qr, kr, vr = [t.detach().clone().requires_grad_(True) for t in (q, k, v)]
         ts = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))

@@ -36,7 +36,7 @@ int main(int argc, char** argv) {
   vmae_att_trace_select(5, 3, B / 2, -1);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    int rc = vmae_attn_fwd(qkv, out, lse, B, L, H, hd, scale, nullptr);
+    int rc = vmae_attn_fwd(qkv, out, lse, B, L, H, hd, scale, 0.f, 0ull, nullptr);
     if (rc) { printf("fwd failed: %s\n", vmae_last_error()); return 1; }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     vmae_att_trace_select(5, 3, B / 2, strcmp(mode, "dq") == 0 ? 0 : 1);
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
-      int rc = vmae_attn_bwd(qkv, out, dout, lse, delta, dqkv, B, L, H, hd, scale, nullptr);
+      int rc = vmae_attn_bwd(qkv, out, dout, lse, delta, dqkv, B, L, H, hd, scale, 0.f, 0ull, nullptr);
       if (rc) { printf("bwd failed: %s\n", vmae_last_error()); return 1; }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
