@@ -293,6 +293,13 @@ extern "C" int vmae_bn_train_bwd(const void* x, const void* dy, const float* gam
 // ==================================================================================================================
 namespace vmae {
 
+// TMA-tiled kernels (dwconv_tma.cu); return 1 when the geometry is not covered (C % 64 != 0), in which case the generic
+// kernels below run instead
+int dwconv_tma_fwd(const void* x, const float* w, void* y, int N, int H, int W, int C, int stride, cudaStream_t stream);
+int dwconv_tma_dgrad_s1(const void* dy, const float* w, void* dx, int N, int H, int W, int C, cudaStream_t stream);
+int dwconv_tma_dgrad_s2(const void* dy, const float* w, void* dx, int N, int H, int W, int C, cudaStream_t stream);
+int dwconv_tma_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int stride, cudaStream_t stream);
+
 struct DwGeom {
   int N, H, W, C, Ho, Wo, stride;
 };
@@ -598,6 +605,8 @@ extern "C" int vmae_dwconv3x3_fwd(const void* x, const float* w, void* y, int N,
   DwGeom g;
   int rc = dw_geom(g, N, H, W, C, stride, "vmae_dwconv3x3_fwd");
   if (rc) return rc;
+  rc = dwconv_tma_fwd(x, w, y, N, H, W, C, stride, (cudaStream_t)stream);
+  if (rc <= 0) return rc;
   dwconv_fwd_kernel<<<dw_grid(C, (long long)N * g.Ho * g.Wo), dim3(16, 16), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, g);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
@@ -609,14 +618,23 @@ extern "C" int vmae_dwconv3x3_bwd(const void* x, const void* dy, const float* w,
   int rc = dw_geom(g, N, H, W, C, stride, "vmae_dwconv3x3_bwd");
   if (rc) return rc;
   if (dx) {
-    dwconv_dgrad_kernel<<<dw_grid(C, (long long)N * H * W), dim3(16, 16), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, g);
-    VMAE_LAUNCH_CHECK();
+    rc = (stride == 1) ? dwconv_tma_dgrad_s1(dy, w, dx, N, H, W, C, (cudaStream_t)stream)
+                       : dwconv_tma_dgrad_s2(dy, w, dx, N, H, W, C, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      dwconv_dgrad_kernel<<<dw_grid(C, (long long)N * H * W), dim3(16, 16), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, g);
+      VMAE_LAUNCH_CHECK();
+    }
   }
   if (dw) {
-    dim3 grid = dw_grid(C, (long long)N * g.Ho * g.Wo);
-    if (grid.y > (unsigned)(num_sms() * 4)) grid.y = num_sms() * 4;
-    dwconv_wgrad_kernel<<<grid, dim3(16, 16), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, g);
-    VMAE_LAUNCH_CHECK();
+    rc = dwconv_tma_wgrad(x, dy, dw, N, H, W, C, stride, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      dim3 grid = dw_grid(C, (long long)N * g.Ho * g.Wo);
+      if (grid.y > (unsigned)(num_sms() * 4)) grid.y = num_sms() * 4;
+      dwconv_wgrad_kernel<<<grid, dim3(16, 16), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, g);
+      VMAE_LAUNCH_CHECK();
+    }
   }
   return VMAE_OK;
 }

@@ -298,7 +298,9 @@ def test_batchnorm_train_fwd_bwd(env, M, Cc, act, res):
     assert relerr(gg.grad, gr.grad) < 2e-2 and relerr(bg.grad, br.grad) < 2e-2
 
 
-@pytest.mark.parametrize("N,H,W,Cc,stride", [(2, 14, 14, 384, 1), (3, 28, 28, 768, 2), (1, 7, 9, 96, 2), (2, 8, 8, 48, 1)])
+@pytest.mark.parametrize("N,H,W,Cc,stride", [(2, 14, 14, 384, 1), (3, 28, 28, 768, 2), (1, 7, 9, 96, 2), (2, 8, 8, 48, 1),
+                                             (2, 56, 56, 128, 1), (2, 56, 56, 64, 2), (1, 60, 61, 64, 1), (1, 57, 117, 64, 2), (3, 5, 3, 64, 1),
+                                             (2, 1, 9, 64, 1), (1, 3, 300, 64, 1)])
 def test_depthwise_conv3x3_fwd_bwd(env, N, H, W, Cc, stride):
     ops, L, dev, g = env
     x = torch.randn(N, H, W, Cc, device=dev, generator=g).bfloat16().requires_grad_(True)
