@@ -5,6 +5,7 @@
 // Replaces cuDNN/ATen ops behind Conv2d_BN, MBConv, SELayer, PatchEmbed (tiny_vit.py:12-72). All kernels are HBM-bound:
 // a thread owns 8 consecutive channels (one 16-byte bf16 vector) so every access is a full, coalesced row segment.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/vmae.h"
 
 namespace vmae {
@@ -51,6 +52,27 @@ __device__ __forceinline__ float cv_gelu_grad(float x) {
   return fmaf(x, 0.39894228040143268f * __expf(-0.5f * x * x), cv_normal_cdf(x));
 }
 
+// gelu'(z) for a pair of lanes on packed FFMA2 (half the issue slots of the scalar form; same polynomial, pdf by one ex2)
+__device__ __forceinline__ void cv_gelu_grad2(float z0, float z1, float& d0, float& d1) {
+  const f32x2 xc2 = pk2(fminf(fmaxf(z0, -4.2f), 4.2f), fminf(fmaxf(z1, -4.2f), 4.2f));
+  const f32x2 u2 = mul2(xc2, xc2);
+  f32x2 q2 = fma2(pk2(5.3164563029728384e-11f), u2, pk2(-5.110036394029294e-09f));
+  q2 = fma2(q2, u2, pk2(2.1774354763692827e-07f));
+  q2 = fma2(q2, u2, pk2(-5.478650564327836e-06f));
+  q2 = fma2(q2, u2, pk2(9.182147914543748e-05f));
+  q2 = fma2(q2, u2, pk2(-0.0010986902052536607f));
+  q2 = fma2(q2, u2, pk2(0.00978302676230669f));
+  q2 = fma2(q2, u2, pk2(-0.0662931576371193f));
+  q2 = fma2(q2, u2, pk2(0.3988766670227051f));
+  const f32x2 cdf2 = fma2(xc2, q2, pk2(0.5f));
+  float e0, e1;
+  up2(fma2(u2, pk2(-0.72134752044448170f), pk2(-1.3257480647361592f)), e0, e1);   // log2(pdf)
+  float p0, p1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+  up2(fma2(xc2, pk2(p0, p1), cdf2), d0, d1);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // BatchNorm kernels. Thread block = (cvec channel-vectors) x (rows): threadIdx.x owns 8 consecutive channels for the whole
 // launch (per-channel parameters live in registers), threadIdx.y walks rows with a grid stride. A row of C channels is
@@ -59,6 +81,7 @@ __device__ __forceinline__ float cv_gelu_grad(float x) {
 // MODE 1: dz = dy * (act ? gelu'(z) : 1), z = xhat*gamma+beta; acc[0][c] += sum dz, acc[1][c] += sum dz*xhat (backward)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int BN_MAX_ROWS_PER_BLOCK = 64;
+constexpr int BN_U = 2;   // rows per pipeline step
 
 template <int MODE>
 __global__ void __launch_bounds__(CV_THREADS) bn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
@@ -76,22 +99,58 @@ __global__ void __launch_bounds__(CV_THREADS) bn_reduce_kernel(const __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; g[j] = gamma[c0 + j]; b[j] = beta[c0 + j]; }
   }
-  for (long long r = (long long)blockIdx.x * ny + threadIdx.y; r < M; r += (long long)gridDim.x * ny) {
-    float xv[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
-    if (MODE == 0) {
+  // software pipeline: BN_U rows per step, and the next BN_U rows are requested before the current ones are consumed
+  // (2 * BN_U rows of HBM traffic in flight per thread; the GELU-gradient arithmetic overlaps the loads)
+  const long long rstep = (long long)gridDim.x * ny;
+  long long r = (long long)blockIdx.x * ny + threadIdx.y;
+  uint4 nxt_x[BN_U], nxt_d[BN_U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
-    } else {
-      float dv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), dv);
+  for (int u = 0; u < BN_U; ++u) {
+    nxt_x[u] = make_uint4(0, 0, 0, 0);
+    nxt_d[u] = make_uint4(0, 0, 0, 0);
+    if (r + u * rstep < M) {
+      nxt_x[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * rstep) * C + c0));
+      if (MODE == 1) nxt_d[u] = __ldg(reinterpret_cast<const uint4*>(dy + (r + u * rstep) * C + c0));
+    }
+  }
+  for (; r < M; r += BN_U * rstep) {
+    uint4 cur_x[BN_U], cur_d[BN_U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (xv[j] - mu[j]) * rs[j];
-        float dz = dv[j];
-        if (act) dz *= cv_gelu_grad(fmaf(xh, g[j], b[j]));
-        a0[j] += dz;
-        a1[j] = fmaf(dz, xh, a1[j]);
+    for (int u = 0; u < BN_U; ++u) { cur_x[u] = nxt_x[u]; cur_d[u] = nxt_d[u]; }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      const long long rn = r + (BN_U + u) * rstep;
+      if (rn < M) {
+        nxt_x[u] = __ldg(reinterpret_cast<const uint4*>(x + rn * C + c0));
+        if (MODE == 1) nxt_d[u] = __ldg(reinterpret_cast<const uint4*>(dy + rn * C + c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      if (r + u * rstep >= M) break;
+      float xv[8];
+      unpack8(cur_x[u], xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
+      } else {
+        float dv[8];
+        unpack8(cur_d[u], dv);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float xh0 = (xv[j] - mu[j]) * rs[j], xh1 = (xv[j + 1] - mu[j + 1]) * rs[j + 1];
+          float dz0 = dv[j], dz1 = dv[j + 1];
+          if (act) {
+            float d0, d1;
+            cv_gelu_grad2(fmaf(xh0, g[j], b[j]), fmaf(xh1, g[j + 1], b[j + 1]), d0, d1);
+            dz0 *= d0;
+            dz1 *= d1;
+          }
+          a0[j] += dz0;
+          a0[j + 1] += dz1;
+          a1[j] = fmaf(dz0, xh0, a1[j]);
+          a1[j + 1] = fmaf(dz1, xh1, a1[j + 1]);
+        }
       }
     }
   }
@@ -138,9 +197,21 @@ __global__ void __launch_bounds__(CV_THREADS) bn_apply_kernel(const __nv_bfloat1
     sc[j] = rstd[c0 + j] * gamma[c0 + j];
     sh[j] = fmaf(-mean[c0 + j], sc[j], beta[c0 + j]);
   }
-  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
+  const long long rstep = (long long)gridDim.x * blockDim.y;
+  long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  uint4 nxt_x = make_uint4(0, 0, 0, 0), nxt_r = make_uint4(0, 0, 0, 0);
+  if (r < M) {
+    nxt_x = __ldg(reinterpret_cast<const uint4*>(x + r * C + c0));
+    if (residual) nxt_r = __ldg(reinterpret_cast<const uint4*>(residual + r * C + c0));
+  }
+  for (; r < M; r += rstep) {
     float xv[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
+    unpack8(nxt_x, xv);
+    const uint4 cur_r = nxt_r;
+    if (r + rstep < M) {   // next row in flight while this one is normalised / activated
+      nxt_x = __ldg(reinterpret_cast<const uint4*>(x + (r + rstep) * C + c0));
+      if (residual) nxt_r = __ldg(reinterpret_cast<const uint4*>(residual + (r + rstep) * C + c0));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(xv[j], sc[j], sh[j]);
@@ -148,7 +219,7 @@ __global__ void __launch_bounds__(CV_THREADS) bn_apply_kernel(const __nv_bfloat1
     }
     if (residual) {
       float rv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(residual + r * C + c0)), rv);
+      unpack8(cur_r, rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += rv[j];
     }
@@ -178,18 +249,52 @@ __global__ void __launch_bounds__(CV_THREADS) bn_bwd_apply_kernel(const __nv_bfl
       if (dgamma) atomicAdd(dgamma + c0 + j, acc[C + c0 + j]);
     }
   }
-  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
-    float xv[8], dv[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), dv);
+  const long long rstep = (long long)gridDim.x * blockDim.y;
+  long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  uint4 nxt_x[BN_U], nxt_d[BN_U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (xv[j] - mu[j]) * rs[j];
-      float dz = dv[j];
-      if (act) dz *= cv_gelu_grad(fmaf(xh, g[j], b[j]));
-      o[j] = g[j] * rs[j] * (dz - s0[j] - xh * s1[j]);
+  for (int u = 0; u < BN_U; ++u) {
+    nxt_x[u] = make_uint4(0, 0, 0, 0);
+    nxt_d[u] = make_uint4(0, 0, 0, 0);
+    if (r + u * rstep < M) {
+      nxt_x[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * rstep) * C + c0));
+      nxt_d[u] = __ldg(reinterpret_cast<const uint4*>(dy + (r + u * rstep) * C + c0));
     }
-    *reinterpret_cast<uint4*>(dx + r * C + c0) = pack8(o);
+  }
+  for (; r < M; r += BN_U * rstep) {
+    uint4 cur_x[BN_U], cur_d[BN_U];
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) { cur_x[u] = nxt_x[u]; cur_d[u] = nxt_d[u]; }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      const long long rn = r + (BN_U + u) * rstep;
+      if (rn < M) {
+        nxt_x[u] = __ldg(reinterpret_cast<const uint4*>(x + rn * C + c0));
+        nxt_d[u] = __ldg(reinterpret_cast<const uint4*>(dy + rn * C + c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      const long long ru = r + u * rstep;
+      if (ru >= M) break;
+      float xv[8], dv[8], o[8];
+      unpack8(cur_x[u], xv);
+      unpack8(cur_d[u], dv);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float xh0 = (xv[j] - mu[j]) * rs[j], xh1 = (xv[j + 1] - mu[j + 1]) * rs[j + 1];
+        float dz0 = dv[j], dz1 = dv[j + 1];
+        if (act) {
+          float d0, d1;
+          cv_gelu_grad2(fmaf(xh0, g[j], b[j]), fmaf(xh1, g[j + 1], b[j + 1]), d0, d1);
+          dz0 *= d0;
+          dz1 *= d1;
+        }
+        o[j] = g[j] * rs[j] * (dz0 - s0[j] - xh0 * s1[j]);
+        o[j + 1] = g[j + 1] * rs[j + 1] * (dz1 - s0[j + 1] - xh1 * s1[j + 1]);
+      }
+      *reinterpret_cast<uint4*>(dx + ru * C + c0) = pack8(o);
+    }
   }
 }
 
