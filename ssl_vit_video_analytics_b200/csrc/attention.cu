@@ -64,6 +64,27 @@ constexpr uint32_t DROP_CQ = 0x9E3779B1u, DROP_CK = 0x85EBCA77u;
 __device__ __forceinline__ uint32_t drop_word(const AttnDrop& d, uint32_t rid, uint32_t kp) {
   return drop_mix32(rid * DROP_CQ + kp * DROP_CK + d.seed_lo) ^ d.seed_hi;
 }
+// 2^x for a pair of lanes on the FMA pipe (the MUFU pipe delivers only 16 ex2 per clock per SM and is the forward kernel's
+// first bound): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial for 2^f (relative error 7.5e-5,
+// far below the bf16 rounding of P), exponent added as an integer. Arguments are clamped at -125 (result ~ 0).
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
+  float lo, hi;
+  up2(x2, lo, hi);
+  x2 = pk2(fmaxf(lo, -125.f), fmaxf(hi, -125.f));
+  const f32x2 t2 = add2(x2, pk2(12582912.f));            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const f32x2 fr2 = fma2(add2(t2, pk2(-12582912.f)), pk2(-1.f), x2);
+  f32x2 p2 = fma2(pk2(0.0551716648f), fr2, pk2(0.2426111251f));
+  p2 = fma2(p2, fr2, pk2(0.6932609677f));
+  p2 = fma2(p2, fr2, pk2(0.9999280572f));
+  float tl, th, pl, ph;
+  up2(t2, tl, th);
+  up2(p2, pl, ph);
+  return pk2(__uint_as_float(__float_as_uint(pl) + (__float_as_uint(tl) << 23)), __uint_as_float(__float_as_uint(ph) + (__float_as_uint(th) << 23)));
+}
+#ifndef VMAE_FWD_POLY_PAIRS
+#define VMAE_FWD_POLY_PAIRS 4
+#endif
+constexpr int FWD_POLY_PAIRS = VMAE_FWD_POLY_PAIRS;   // of every 16 column pairs, this many take the polynomial instead of MUFU (measured optimum 5-6)
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -285,15 +306,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float msl = m * sl2;
       ATT_STAMP(0, j, 3);
       ATT_STAMP(0, j, 4);
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      f32x2 l4[4] = {0ull, 0ull, 0ull, 0ull};
+      const f32x2 sl2_2 = pk2(sl2), nmsl_2 = pk2(-msl);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         // packed in place (slot i/2 has already been consumed when pair i is written): no second register array
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(sc[c][i]), sl2, -msl));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sc[c][i + 1]), sl2, -msl));
-          l4[c] += p0 + p1;   // the normaliser sums the un-dropped probabilities
+          const f32x2 x2 = fma2(pk2(__uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1])), sl2_2, nmsl_2);
+          f32x2 p2;
+          if ((((i >> 1) * FWD_POLY_PAIRS) & 15) < FWD_POLY_PAIRS) {   // FWD_POLY_PAIRS of 16 pairs, evenly spread
+            p2 = exp2_poly2(x2);
+          } else {
+            float a, b2;
+            up2(x2, a, b2);
+            p2 = pk2(ex2_approx(a), ex2_approx(b2));
+          }
+          l4[c] = add2(l4[c], p2);   // the normaliser sums the un-dropped probabilities
+          float p0, p1;
+          up2(p2, p0, p1);
           if (DROP) {
             const uint32_t w = drop_mix32(drop_base + static_cast<uint32_t>((j * BKV + c * 32 + i) >> 1) * DROP_CK) ^ drop.seed_hi;
             if ((w & 0xffffu) < drop.thr) p0 = 0.f;
@@ -302,7 +333,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           sc[c][i >> 1] = pack_bf16x2(p0, p1);
         }
       }
-      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      {
+        float a, b2;
+        up2(add2(add2(l4[0], l4[1]), add2(l4[2], l4[3])), a, b2);
+        l += a + b2;
+      }
       // P_j stays in registers until P_{j-1} V_{j-1} has retired (its P operand and its K/V stage are then free). Waiting
       // here instead of before the exponentials takes the MMA round trip (observe p_ready, issue, execute behind the
       // other CTA's MMAs, commit) off the critical path: by now it finished ~1000 cycles ago.
