@@ -25,7 +25,7 @@ SIGNATURES = {
     "vmae_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "vmae_linear_wgrad": [_p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _i, _p],
     "vmae_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
-    "vmae_attn_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
+    "vmae_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
     "vmae_attn_dropout_mask": [_p, _i, _i, _i, _f, _ull, _p],
     "vmae_dropout_apply": [_p, _i, _p, _p, _i, _ll, _f, _ull, _p],
     "vmae_dropout_mask": [_p, _ll, _f, _ull, _p],

@@ -17,20 +17,7 @@
 
 namespace vmae {
 
-#ifdef VMAE_ATT_TRACE
-// developer timeline (tools/trace_attn.cu): clock64 stamps of one CTA, [role 0 = row warp 2 lane 0 | 1 = MMA thread][iteration][slot]
-__device__ long long g_att_trace[2 * 32 * 8];
-__device__ int g_att_trace_cta[4];   // block x, y, z, backward mode filter (-1 = any)
-#define ATT_TRACE_INIT()                                                                                               \
-  const bool att_traced = blockIdx.x == g_att_trace_cta[0] && blockIdx.y == g_att_trace_cta[1] && blockIdx.z == g_att_trace_cta[2]
-#define ATT_STAMP(role, it, slot)                                                                                      \
-  do {                                                                                                                 \
-    if (att_traced && (it) < 32 && ((role) == 1 || threadIdx.x == 128)) g_att_trace[((role) * 32 + (it)) * 8 + (slot)] = clock64(); \
-  } while (0)
-#else
-#define ATT_TRACE_INIT() do { } while (0)
-#define ATT_STAMP(role, it, slot) do { } while (0)
-#endif
+#include "att_trace.cuh"
 
 constexpr int ATT_FWD_THREADS = 256;  // all kernels: warpgroup 0 = control (warp 0 UMMA issuer, warp 1 TMA producer), warpgroup 1 = one thread per row
 // Two CTAs per SM leave 128 registers per thread at launch; the control warpgroup shrinks to ATT_CTRL_REGS and the row
@@ -798,13 +785,8 @@ __global__ void __launch_bounds__(256) attn_dropout_mask_kernel(uint8_t* __restr
 using namespace vmae;
 
 #ifdef VMAE_ATT_TRACE
-extern "C" int vmae_att_trace_select(int bx, int by, int bz, int mode) {
-  int h[4] = {bx, by, bz, mode};
-  cudaMemcpyToSymbol(g_att_trace_cta, h, sizeof(h));
-  static long long zero[2 * 32 * 8] = {0};
-  return (int)cudaMemcpyToSymbol(g_att_trace, zero, sizeof(zero));
-}
-extern "C" int vmae_att_trace_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_att_trace, sizeof(long long) * 2 * 32 * 8); }
+extern "C" int vmae_att_trace_select(int bx, int by, int bz, int mode) { return att_trace_select_tu(bx, by, bz, mode); }
+extern "C" int vmae_att_trace_read(long long* host) { return att_trace_read_tu(host); }
 #endif
 
 extern "C" int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, float p_drop,
@@ -829,8 +811,13 @@ extern "C" int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_d
   return VMAE_OK;
 }
 
-extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
-                             int L, int H, int hd, float scale, float p_drop, unsigned long long seed, void* stream) {
+namespace vmae {
+int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* dq_accum, int B, int L, int H,
+                        float scale, cudaStream_t stream);   // attention_bwd_fused.cu
+}
+
+extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum, void* dqkv,
+                             int B, int L, int H, int hd, float scale, float p_drop, unsigned long long seed, void* stream) {
   VMAE_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vmae_attn_bwd: null pointer");
   VMAE_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "vmae_attn_bwd: p_drop=%f outside [0, 1)", (double)p_drop);
   VMAE_CHECK_ARG((long long)B * H * L < (1LL << 32), "vmae_attn_bwd: B*H*L must fit 32 bits");
@@ -844,6 +831,9 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
   if (hd == 64) {
     attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
     VMAE_LAUNCH_CHECK();
+    // single-pass kernel (5 GEMM units, one exponential per score, dQ reduced through L2) when the caller provides the fp32
+    // dQ accumulator; the two-kernel form otherwise and whenever dropout is active
+    if (dq_accum != nullptr && p_drop == 0.f) return attn_bwd_fused_hd64(qkv, dout, lse, delta, dqkv, dq_accum, B, L, H, scale, s);
     rc = launch_bwd<64, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
     if (rc) return rc;
     return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);

@@ -1,0 +1,463 @@
+// K2 — single-pass flash-attention backward for head_dim 64 (the decoder / ViT-S shape), tcgen05 + TMEM, sm_100a.
+//
+// The two-kernel backward in attention.cu recomputes S and dP twice (7 GEMM units and 2 exponentials per score). This kernel
+// does the textbook 5 units and 1 exponential: a CTA owns 128 key/value rows (dK, dV accumulate in TMEM over the whole
+// query sweep) and, per 128-query block, also produces that block's partial dQ = dS K, which is added to an fp32
+// accumulator in global memory with TMA reduce-add (L2 atomics, 32 KB per block). One CTA per SM (it needs 512 TMEM
+// columns); 384 threads = a control warpgroup (TMA producer warp, UMMA issuer warp; shrunk to 40 registers) and eight row warps (a thread owns one key row / TMEM lane and
+// half of the query columns, so every SM sub-partition has two row warps whose phases overlap).
+//
+//   per query block i:   T0 = K Q_i^T   (S^T, 128 x 128)          T1 = V dO_i^T   (dP^T)
+//                        P^T = exp2(T0 * scale*log2e - lse_i),     dS^T = P^T * (T1 - delta_i)
+//                        dV += P^T dO_i   (A operand = P^T in TMEM)      dK += dS^T Q_i   (A = dS^T tile in smem, K-major)
+//                        dQ_i = dS K      (A = the same smem tile read MN-major: no transpose pass)
+// The per-column statistics (lse_i, delta_i) are staged in warp-private double-buffered shared arrays; the row warps never meet
+// at a CTA-wide barrier: they synchronise only through the mbarriers they share with the UMMA warp.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/vmae.h"
+
+namespace vmae {
+
+#include "att_trace.cuh"
+
+namespace fb {
+constexpr int HD = 64;
+constexpr int BQ = 128;                    // query rows per block (columns of the score tiles)
+constexpr int THREADS = 384;               // warpgroup 0: TMA warp, UMMA warp (+2 idle); warpgroups 1, 2: 8 row warps
+constexpr int CTRL_REGS = 64, ROW_REGS = 216;   // setmaxnreg: 128 x 64 + 256 x 216 = 63488 <= 384 x 168 registers
+constexpr int NS = 3;                      // Q/dO ring depth
+constexpr int TILE = 128 * HD * 2;         // one [128 x 64] bf16 operand tile: 16 KB
+constexpr int OFF_K = 0;
+constexpr int OFF_V = OFF_K + TILE;
+constexpr int OFF_Y = OFF_V + TILE;        // [NS][2] tiles: Q_i, dO_i
+constexpr int OFF_E = OFF_Y + NS * 2 * TILE;       // dS^T: [128 key rows x 128 queries] bf16 = two 64-column SW128 chunks (32 KB)
+constexpr int OFF_DQ = OFF_E + 2 * TILE;           // dQ staging: two [128 x 32] fp32 SW128 boxes (32 KB)
+constexpr int OFF_STAT = OFF_DQ + 2 * TILE;        // per row warp: [2 buffers][lse*log2e (64) | delta (64)] fp32 = 1 KB; 8 warps
+constexpr int OFF_BAR = OFF_STAT + 8 * 2 * 128 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
+// TMEM columns
+constexpr uint32_t T0 = 0, T1 = 128, DK = 256, DV = 320, DQ = 384, TP = 448;
+constexpr float LOG2E_F = 1.4426950408889634f;
+}  // namespace fb
+
+__device__ __forceinline__ float fb_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t fb_pack(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void fb_sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void fb_sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void fb_tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// map_qkv: 128-row boxes over qkv (K/V resident per work item, Q streamed); map_do: 128-row boxes over dO;
+// map_dq: fp32 [B, L, H*64], box 32 x 128.
+// Persistent: grid = #SMs; a CTA walks work items w = (b, h, key tile) with stride gridDim.x (consecutive items share (b, h),
+// so co-running CTAs stream the same Q_i / dO_i blocks out of L2). TMEM is allocated once, the mbarrier phases run on across
+// items, and the next item's K/V load overlaps the current item's dK/dV read-out.
+__global__ void __launch_bounds__(fb::THREADS, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                      const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ lse, const float* __restrict__ delta,
+                      __nv_bfloat16* __restrict__ dqkv, int L, int H, int B, float scale) {
+  using namespace fb;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (threadIdx.x == 0 && (sbase & 1023u) != 0) { printf("vmae attention: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+  const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V, sE = sbase + OFF_E, sDQ = sbase + OFF_DQ;
+  auto sY = [&](int s, int t) { return sbase + OFF_Y + (s * 2 + t) * TILE; };
+  float* stat = reinterpret_cast<float*>(smem_raw + OFF_STAT);
+  const uint32_t bar = sbase + OFF_BAR;
+  const uint32_t res_full = bar, t_full = bar + 8, t_free = bar + 16, p_ready = bar + 24, acc_done = bar + 32, kv_free = bar + 104;
+  auto st_full = [&](int s) { return bar + 40 + 8 * s; };
+  auto st_empty = [&](int s) { return bar + 64 + 8 * s; };
+  const uint32_t tmem_ptr_addr = bar + 96;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int niter = (L + BQ - 1) / BQ;
+  const int ntiles = (L + 127) / 128;
+  const int total = B * H * ntiles;
+  auto decode = [&](int w, int& b, int& h, int& r0) {
+    r0 = (w % ntiles) * 128;
+    h = (w / ntiles) % H;
+    b = w / (ntiles * H);
+  };
+#ifdef VMAE_ATT_TRACE
+  const bool att_cta = static_cast<int>(blockIdx.x) == g_att_trace_cta[0];
+  bool att_traced = false;   // set per work item: the stamps of item number g_att_trace_cta[1] of that CTA are kept
+#define FB_TRACE_ITEM(n) att_traced = att_cta && static_cast<int>(n) == g_att_trace_cta[1]
+#else
+#define FB_TRACE_ITEM(n) do { } while (0)
+#endif
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_dq);
+    mbar_init(res_full, 1);
+    mbar_init(t_full, 1);
+    mbar_init(t_free, 8);
+    mbar_init(p_ready, 8);
+    mbar_init(acc_done, 1);
+    mbar_init(kv_free, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_addr, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+
+  if (warp < 4) {
+    setmaxnreg_dec<CTRL_REGS>();
+  if (warp == 0) {
+    if (elect_one()) {   // TMA producer
+      uint32_t gi = 0, item_n = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++item_n) {
+        int b, h, r0;
+        decode(w, b, h, r0);
+        if (item_n > 0) mbar_wait(kv_free, (item_n - 1) & 1);   // the previous item's last MMAs have finished reading K / V
+        mbar_expect_tx(res_full, 2 * TILE);
+        tma_load_3d(sK, &map_qkv, res_full, (H + h) * HD, r0, b);
+        tma_load_3d(sV, &map_qkv, res_full, (2 * H + h) * HD, r0, b);
+        for (int it = 0; it < niter; ++it, ++gi) {
+          const int s = gi % NS;
+          mbar_wait(st_empty(s), ((gi / NS) & 1) ^ 1u);
+          mbar_expect_tx(st_full(s), 2 * TILE);
+          tma_load_3d(sY(s, 0), &map_qkv, st_full(s), h * HD, it * BQ, b);   // Q_i
+          tma_load_3d(sY(s, 1), &map_do, st_full(s), h * HD, it * BQ, b);    // dO_i
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {   // UMMA issuer
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, BQ, 0, 0);    // T = A(K-major) x B(K-major), N = 128
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);    // acc += A(K-major | TMEM) x B(MN-major), N = 64
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 1, 1);    // dQ = A(MN-major) x B(MN-major)
+      const uint64_t dK_k = umma_smem_desc(sK, 0, 1024, 128);         // K as K-major A (and, advanced by rows, as MN-major B)
+      const uint64_t dV_k = umma_smem_desc(sV, 0, 1024, 128);
+      uint64_t dQ_[NS], dO_[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        dQ_[s] = umma_smem_desc(sY(s, 0), 0, 1024, 128);
+        dO_[s] = umma_smem_desc(sY(s, 1), 0, 1024, 128);
+      }
+      const uint64_t dE_k = umma_smem_desc(sE, 0, 1024, 128);             // dS^T, K-major: 64-query chunks 16 KB apart
+      const uint64_t dE_mn = umma_smem_desc(sE, 128 * 128, 1024, 128);    // dS, MN-major: LBO = stride between the two 64-wide M chunks
+      auto issue_t = [&](uint32_t g) {
+        const int s = g % NS;
+        mbar_wait(st_full(s), (g / NS) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T0, dK_k + 2 * k, dQ_[s] + 2 * k, idesc_t, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T1, dV_k + 2 * k, dO_[s] + 2 * k, idesc_t, k > 0);
+        umma_commit(t_full);
+      };
+      uint32_t gi = 0, item_n = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++item_n) {
+        FB_TRACE_ITEM(item_n);
+        mbar_wait(res_full, item_n & 1);
+        if (gi > 0) { mbar_wait(t_free, (gi - 1) & 1); }   // the rows have pulled the previous item's last score tiles out of TMEM
+        tc_fence_after();
+        issue_t(gi);
+        for (int it = 0; it < niter; ++it, ++gi) {
+          const int s = gi % NS;
+          ATT_STAMP(1, it, 0);
+          if (it + 1 < niter) {   // the rows hold T(it) in registers: T(it+1) is computed underneath their element-wise phase
+            mbar_wait(t_free, gi & 1);
+            tc_fence_after();
+            ATT_STAMP(1, it, 1);
+            issue_t(gi + 1);
+          }
+          ATT_STAMP(1, it, 2);
+          mbar_wait(p_ready, gi & 1);   // P^T(it) is in TMEM, dS^T(it) in shared memory
+          tc_fence_after();
+          ATT_STAMP(1, it, 3);
+#pragma unroll
+          for (int kk = 0; kk < BQ / 16; ++kk)   // dV += P^T dO_i  (contraction over the 128 queries)
+            umma_bf16_ts(tmem + DV, tmem + TP + kk * 8, dO_[s] + kk * 128, idesc_a, (it > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < BQ / 16; ++kk)   // dK += dS^T Q_i
+            umma_bf16(tmem + DK, dE_k + (kk >> 2) * 1024 + 2 * (kk & 3), dQ_[s] + kk * 128, idesc_a, (it > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < 128 / 16; ++kk)  // dQ_i = dS K      (contraction over the 128 keys of this CTA)
+            umma_bf16(tmem + DQ, dE_mn + kk * 128, dK_k + kk * 128, idesc_q, kk > 0);
+          umma_commit(st_empty(s));
+          umma_commit(acc_done);
+          if (it + 1 == niter) umma_commit(kv_free);
+          ATT_STAMP(1, it, 4);
+        }
+      }
+    }
+  }
+  } else {
+    setmaxnreg_inc<ROW_REGS>();
+    // Eight row warps = two groups of four: a thread owns key row `row` (= TMEM lane) and the 64 query columns of its group's half
+    // of every score tile, so each sub-partition has two row warps whose phases overlap. Group g also owns columns
+    // [32g, 32g+32) of each dQ tile and, in the item tail, dK (g = 0) or dV (g = 1).
+    const int grp = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int tid = threadIdx.x - 128;      // 0..255 among the row threads
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float sl2 = scale * LOG2E_F;
+    // Column statistics (lse_i, delta_i) of this group's 64 query columns live in a warp-private, double-buffered shared array:
+    // lanes 0..15 fetch four lse values each, lanes 16..31 four delta values, so the row warps never meet at a CTA barrier.
+    // The loads are unconditional (clamped index) and nothing touches their results until they are deposited one iteration
+    // later: a select or multiply right behind the load would stall the warp for the full DRAM latency.
+    float* wstat = stat + (warp - 4) * 2 * 128;
+    const float* stat_src = (lane < 16) ? lse : delta;
+    const int sc0 = grp * 64 + (lane & 15) * 4;   // first of this lane's four columns inside the query block
+    auto fetch_stat = [&](int b, int h, int it, float (&v)[4]) {
+      const float* base = stat_src + (static_cast<long long>(b) * H + h) * L;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldg(base + min(it * BQ + sc0 + j, L - 1));
+    };
+    auto deposit_stat = [&](uint32_t g, int it, const float (&v)[4]) {   // lse * log2(e), +inf past the end (p == 0); delta, 0 past the end
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = it * BQ + sc0 + j < L;
+        o[j] = (lane < 16) ? (in ? v[j] * LOG2E_F : INFINITY) : (in ? v[j] : 0.f);
+      }
+      *reinterpret_cast<float4*>(wstat + (g & 1) * 128 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);   // lanes 16..31 land in [64, 128)
+    };
+
+    // read this warp's 32 rows x 32 columns of a finished dQ tile and add them to the global accumulator (one TMA reduce per warp)
+    const uint32_t my_box = sDQ + grp * TILE + quad * 32 * 128;
+    auto flush_dq = [&](int b, int h, int qb) {
+      uint32_t r[32];
+      tmem_ld32(tmem + DQ + lane_off + grp * 32, r);
+      tmem_wait_ld();
+      if (lane == 0) tma_store_wait_read<0>();   // this warp's previous reduction has read its staging box
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        fb_sts_f4(my_box + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        fb_tma_reduce_add_3d(&map_dq, my_box, h * HD + grp * 32, qb * BQ + quad * 32, b);
+        tma_store_commit();
+      }
+    };
+
+    uint32_t gi = 0;
+    if (static_cast<int>(blockIdx.x) < total) {
+      int b, h, r0;
+      decode(blockIdx.x, b, h, r0);
+      float v[4];
+      fetch_stat(b, h, 0, v);
+      deposit_stat(0, 0, v);
+    }
+    __syncwarp();
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      int b, h, r0;
+      decode(w, b, h, r0);
+      const int g_row = r0 + row;
+      FB_TRACE_ITEM((w - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x));
+      for (int it = 0; it < niter; ++it, ++gi) {
+        // statistics of the next query block (of this item, or the first block of the next item)
+        float nxt_stat[4] = {0.f, 0.f, 0.f, 0.f};
+        bool has_next = true;
+        int nit = it + 1;
+        {
+          int nb = b, nh = h, nr0;
+          if (nit == niter) {
+            nit = 0;
+            if (w + static_cast<int>(gridDim.x) < total) decode(w + gridDim.x, nb, nh, nr0); else has_next = false;
+          }
+          if (has_next) fetch_stat(nb, nh, nit, nxt_stat);
+        }
+        ATT_STAMP_T(0, it, 0, 128);
+        const float* st_lse = wstat + (gi & 1) * 128;
+        const float* st_delta = st_lse + 64;
+        ATT_STAMP_T(0, it, 1, 128);
+        mbar_wait(t_full, gi & 1);
+        tc_fence_after();
+        ATT_STAMP_T(0, it, 2, 128);
+        uint32_t ts[2][32], tp[2][32];   // this group's 64 columns of T0 (scores) and T1 (dP) of this key row
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tmem + T0 + lane_off + grp * 64 + c * 32, ts[c]);
+          tmem_ld32(tmem + T1 + lane_off + grp * 64 + c * 32, tp[c]);
+        }
+        tmem_wait_ld();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(t_free);   // the tiles are in registers: T(it+1) is computed underneath the element-wise phase
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c * 32 + 4 * i4);
+            const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c * 32 + 4 * i4);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = 4 * i4 + t;
+              const float p = fb_ex2(fmaf(__uint_as_float(ts[c][i]), sl2, -lv[t]));
+              ts[c][i] = __float_as_uint(p);
+              tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - dv[t]));
+            }
+          }
+        ATT_STAMP_T(0, it, 3, 128);
+        if (it > 0) {
+          // the MMAs of the previous block have retired: its dQ tile is complete, and P^T / dS^T may be overwritten
+          mbar_wait(acc_done, (gi - 1) & 1);
+          tc_fence_after();
+          ATT_STAMP_T(0, it, 4, 128);
+          flush_dq(b, h, it - 1);
+          ATT_STAMP_T(0, it, 5, 128);
+        }
+        // P^T half -> TMEM operand (32 packed columns), dS^T half -> shared-memory tile chunk `grp`
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = fb_pack(__uint_as_float(ts[c][2 * i]), __uint_as_float(ts[c][2 * i + 1]));
+          tmem_st16(tmem + TP + lane_off + grp * 32 + c * 16, u);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t row_base = sE + grp * TILE + row * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t addr = row_base + ((((c * 32) >> 3) + i) ^ (row & 7)) * 16;
+            fb_sts_u4(addr, fb_pack(__uint_as_float(tp[c][8 * i]), __uint_as_float(tp[c][8 * i + 1])),
+                      fb_pack(__uint_as_float(tp[c][8 * i + 2]), __uint_as_float(tp[c][8 * i + 3])),
+                      fb_pack(__uint_as_float(tp[c][8 * i + 4]), __uint_as_float(tp[c][8 * i + 5])),
+                      fb_pack(__uint_as_float(tp[c][8 * i + 6]), __uint_as_float(tp[c][8 * i + 7])));
+          }
+        }
+        ATT_STAMP_T(0, it, 6, 128);
+        tmem_wait_st();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        ATT_STAMP_T(0, it, 7, 128);
+        if (has_next) deposit_stat(gi + 1, nit, nxt_stat);   // the other buffer: this warp finished reading it an iteration ago
+        __syncwarp();
+      }
+      // item tail: last dQ tile, then the dK / dV accumulators of this key tile (the producer is already loading the next K / V)
+      ATT_STAMP_T(0, niter, 0, 128);
+      mbar_wait(acc_done, (gi - 1) & 1);
+      tc_fence_after();
+      ATT_STAMP_T(0, niter, 1, 128);
+      flush_dq(b, h, niter - 1);
+      ATT_STAMP_T(0, niter, 2, 128);
+      const long long row_off = (static_cast<long long>(b) * L + g_row) * (3 * H * HD);
+      uint32_t ra[2][32];   // group 0: dK, group 1: dV (2 x 32 columns): both loads in flight, one wait
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tmem_ld32(tmem + (grp == 0 ? DK : DV) + lane_off + c * 32, ra[c]);
+      tmem_wait_ld();
+      if (g_row < L) {
+        const float f = (grp == 0) ? scale : 1.0f;   // dS was accumulated without the softmax scale
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          __nv_bfloat16* dst = dqkv + row_off + ((grp + 1) * H + h) * HD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk;
+            pk.x = fb_pack(__uint_as_float(ra[c][i]) * f, __uint_as_float(ra[c][i + 1]) * f);
+            pk.y = fb_pack(__uint_as_float(ra[c][i + 2]) * f, __uint_as_float(ra[c][i + 3]) * f);
+            pk.z = fb_pack(__uint_as_float(ra[c][i + 4]) * f, __uint_as_float(ra[c][i + 5]) * f);
+            pk.w = fb_pack(__uint_as_float(ra[c][i + 6]) * f, __uint_as_float(ra[c][i + 7]) * f);
+            *reinterpret_cast<uint4*>(dst + i) = pk;
+          }
+        }
+      }
+      ATT_STAMP_T(0, niter, 3, 128);
+    }
+    if (lane == 0) tma_store_wait<0>();   // this warp's bulk reductions have completed before the CTA retires
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// dq (bf16, q slot of dqkv[B, L, 3, H, 64]) = scale * dq_accum (fp32 [B, L, H*64])
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H,
+                                                              float scale) {
+  const int vec_per_row = H * fb::HD / 4;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += gridDim.x * 256LL) {
+    const long long r = idx / vec_per_row;
+    const int c = static_cast<int>(idx % vec_per_row) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(acc + r * (H * fb::HD) + c));
+    uint2 u;
+    u.x = fb_pack(v.x * scale, v.y * scale);
+    u.y = fb_pack(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(dqkv + r * (3 * H * fb::HD) + c) = u;
+  }
+}
+
+#ifdef VMAE_ATT_TRACE
+int att_trace_select_fused(int bx, int by, int bz) { return att_trace_select_tu(bx, by, bz, -1); }
+int att_trace_read_fused(long long* host) { return att_trace_read_tu(host); }
+#endif
+
+// Returns 0 on success, <0 on error. dq_accum: fp32 [B, L, H*64] workspace (zeroed here).
+int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* dq_accum, int B, int L, int H,
+                        float scale, cudaStream_t stream) {
+  using namespace fb;
+  CUtensorMap m_qkv, m_do, m_dq;
+  {
+    const uint64_t dims[3] = {(uint64_t)3 * H * HD, (uint64_t)L, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)3 * H * HD * 2, (uint64_t)L * 3 * H * HD * 2};
+    const uint32_t box[3] = {(uint32_t)HD, 128, 1};
+    int rc = make_tmap_bf16(&m_qkv, qkv, 3, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)H * HD * 2, (uint64_t)L * H * HD * 2};
+    const uint32_t box[3] = {(uint32_t)HD, 128, 1};
+    int rc = make_tmap_bf16(&m_do, dout, 3, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)H * HD * 4, (uint64_t)L * H * HD * 4};
+    const uint32_t box[3] = {32, 32, 1};   // one reduction per row warp: 32 query rows x 32 head-dim columns
+    int rc = make_tmap(&m_dq, dq_accum, VMAE_DTYPE_F32, 3, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  VMAE_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * L * H * HD * sizeof(float), stream));
+  VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long items = (long long)B * H * ((L + 127) / 128);
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_bwd_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale);
+  VMAE_LAUNCH_CHECK();
+  const long long rows = (long long)B * L;
+  long long g = (rows * (H * HD / 4) + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  attn_dq_convert_kernel<<<(unsigned)g, 256, 0, stream>>>(dq_accum, (__nv_bfloat16*)dqkv, rows, H, scale);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+}  // namespace vmae
+
+#ifdef VMAE_ATT_TRACE
+extern "C" int vmae_att_trace_select_fused(int bx, int by, int bz) { return vmae::att_trace_select_fused(bx, by, bz); }
+extern "C" int vmae_att_trace_read_fused(long long* host) { return vmae::att_trace_read_fused(host); }
+#endif

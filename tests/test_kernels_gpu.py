@@ -115,7 +115,7 @@ def _ref_attn(qkv, H):
 
 
 @pytest.mark.parametrize("B,Lq,H,hd", [(1, 16, 1, 64), (1, 64, 1, 64), (1, 100, 2, 64), (2, 160, 6, 64), (2, 300, 3, 64), (2, 1568, 6, 64),
-                                       (1, 128, 1, 32), (3, 196, 12, 32), (2, 784, 6, 32), (1, 49, 18, 32)])
+                                       (9, 520, 7, 64), (1, 128, 1, 32), (3, 196, 12, 32), (2, 784, 6, 32), (1, 49, 18, 32)])
 def test_flash_attention_fwd_bwd(env, B, Lq, H, hd):
     ops, L, dev, g = env
     qkv = torch.randn(B, Lq, 3 * H * hd, device=dev, generator=g).bfloat16()
@@ -125,11 +125,13 @@ def test_flash_attention_fwd_bwd(env, B, Lq, H, hd):
     ro, rl = _ref_attn(qf, H)
     assert relerr(out.view(B, Lq, -1), ro) < BF16_TOL
     assert float((lse - rl).abs().max()) < 1e-2
-    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)
     ro.backward(dout.float().view(B, Lq, -1))
-    for i, name in enumerate("qkv"):
-        sl = slice(i * H * hd, (i + 1) * H * hd)
-        assert relerr(dqkv[..., sl], qf.grad[..., sl]) < 2.5e-2, name
+    # both backward implementations: the two-kernel form (every head_dim) and the single-pass kernel (head_dim 64)
+    for fused in ([False, True] if hd == 64 else [False]):
+        dqkv = ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, fused=fused)
+        for i, name in enumerate("qkv"):
+            sl = slice(i * H * hd, (i + 1) * H * hd)
+            assert relerr(dqkv[..., sl], qf.grad[..., sl]) < 2.5e-2, (name, fused)
 
 
 def test_attention_rejects_unsupported_head_dim(env):

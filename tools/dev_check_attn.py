@@ -11,6 +11,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ssl_vit_video_analytics_b200 import _lib as L  # noqa: E402
 
 lib = L.load()
+FUSED = "--two-kernel" not in sys.argv   # single-pass backward (head_dim 64) unless --two-kernel is given
 dev = torch.device("cuda:0")
 
 
@@ -69,7 +70,8 @@ def mode_bwd():
         L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_fwd")
         dqkv = torch.full_like(qkv, float("nan"))
         delta = torch.empty(B, H, Lq, device=dev, dtype=torch.float32)
-        L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_bwd")
+        dqacc = torch.empty(B, Lq, H * hd, device=dev, dtype=torch.float32) if (FUSED and hd == 64) else None
+        L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "attn_bwd")
         torch.cuda.synchronize()
         qf = qkv.float().requires_grad_(True)
         ro, _ = ref_attn(qf, scale)
@@ -91,6 +93,7 @@ def mode_perf():
         lse = torch.empty(B, H, Lq, device=dev, dtype=torch.float32)
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(B, H, Lq, device=dev, dtype=torch.float32)
+        dqacc = torch.empty(B, Lq, H * hd, device=dev, dtype=torch.float32) if (FUSED and hd == 64) else None
         flops_f = 4.0 * B * H * Lq * Lq * hd
 
         def timeit(fn, iters=5):
@@ -106,7 +109,7 @@ def mode_perf():
             return e0.elapsed_time(e1) / iters
 
         tf = timeit(lambda: L.check(lib.vmae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, Lq, H, hd, scale, 0.0, 0, stream()), "f"))
-        tb = timeit(lambda: L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "b"))
+        tb = timeit(lambda: L.check(lib.vmae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqacc), ptr(dqkv), B, Lq, H, hd, scale, 0.0, 0, stream()), "b"))
         q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
         qr, kr, vr = [t.detach().clone().requires_grad_(True) for t in (q, k, v)]
         ts = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))

@@ -12,6 +12,8 @@
 
 extern "C" int vmae_att_trace_select(int bx, int by, int bz, int mode);
 extern "C" int vmae_att_trace_read(long long* host);
+extern "C" int vmae_att_trace_select_fused(int bx, int by, int bz);
+extern "C" int vmae_att_trace_read_fused(long long* host);
 
 __global__ void fill(__nv_bfloat16* p, long long n, unsigned seed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -26,9 +28,9 @@ int main(int argc, char** argv) {
   int B = argc > 2 ? atoi(argv[2]) : 16, L = argc > 3 ? atoi(argv[3]) : 1568, H = 6, hd = 64;
   long long nq = (long long)B * L * 3 * H * hd, no = (long long)B * L * H * hd;
   __nv_bfloat16 *qkv, *out, *dout, *dqkv;
-  float *lse, *delta;
+  float *lse, *delta, *dqacc;
   cudaMalloc(&qkv, nq * 2); cudaMalloc(&out, no * 2); cudaMalloc(&dout, no * 2); cudaMalloc(&dqkv, nq * 2);
-  cudaMalloc(&lse, (long long)B * H * L * 4); cudaMalloc(&delta, (long long)B * H * L * 4);
+  cudaMalloc(&lse, (long long)B * H * L * 4); cudaMalloc(&delta, (long long)B * H * L * 4); cudaMalloc(&dqacc, no * 4);
   fill<<<1024, 256>>>(qkv, nq, 1u);
   fill<<<1024, 256>>>(dout, no, 7u);
   float scale = 0.125f;
@@ -44,10 +46,12 @@ int main(int argc, char** argv) {
     if (rep == 2) printf("fwd B=%d L=%d: %.1f us\n", B, L, ms * 1e3);
   }
   if (strcmp(mode, "fwd") != 0) {
+    const bool fused = strcmp(mode, "fused") == 0;
     vmae_att_trace_select(5, 3, B / 2, strcmp(mode, "dq") == 0 ? 0 : 1);
+    if (fused) vmae_att_trace_select_fused(70, 12, 0);   // persistent kernel: CTA index, work-item number of that CTA
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
-      int rc = vmae_attn_bwd(qkv, out, dout, lse, delta, dqkv, B, L, H, hd, scale, 0.f, 0ull, nullptr);
+      int rc = vmae_attn_bwd(qkv, out, dout, lse, delta, fused ? dqacc : nullptr, dqkv, B, L, H, hd, scale, 0.f, 0ull, nullptr);
       if (rc) { printf("bwd failed: %s\n", vmae_last_error()); return 1; }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
@@ -58,7 +62,7 @@ int main(int argc, char** argv) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("cuda error: %s\n", cudaGetErrorString(e)); return 1; }
   std::vector<long long> t(2 * 32 * 8);
-  vmae_att_trace_read(t.data());
+  if (strcmp(mode, "fused") == 0) vmae_att_trace_read_fused(t.data()); else vmae_att_trace_read(t.data());
   long long base = 0;
   for (long long v : t) if (v > 0 && (base == 0 || v < base)) base = v;
   for (int role = 0; role < 2; ++role) {
