@@ -47,6 +47,23 @@ __device__ __forceinline__ float fb_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for two lanes on the FMA pipe (see attention.cu): degree-3 minimax polynomial, relative error 7.5e-5
+__device__ __forceinline__ void fb_exp2_poly2(float x0, float x1, float& y0, float& y1) {
+  const f32x2 x2 = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const f32x2 t2 = add2(x2, pk2(12582912.f));
+  const f32x2 fr2 = fma2(add2(t2, pk2(-12582912.f)), pk2(-1.f), x2);
+  f32x2 p2 = fma2(pk2(0.0551716648f), fr2, pk2(0.2426111251f));
+  p2 = fma2(p2, fr2, pk2(0.6932609677f));
+  p2 = fma2(p2, fr2, pk2(0.9999280572f));
+  float tl, th, pl, ph;
+  up2(t2, tl, th);
+  up2(p2, pl, ph);
+  y0 = __uint_as_float(__float_as_uint(pl) + (__float_as_uint(tl) << 23));
+  y1 = __uint_as_float(__float_as_uint(ph) + (__float_as_uint(th) << 23));
+}
+#ifndef VMAE_FB_POLY
+#define VMAE_FB_POLY 0   // of every 8 column quads, this many take the polynomial exp2 (measured: no gain here, the phase is not MUFU-bound)
+#endif
 __device__ __forceinline__ uint32_t fb_pack(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -223,8 +240,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     float* wstat = stat + (warp - 4) * 2 * 128;
     const float* stat_src = (lane < 16) ? lse : delta;
     const int sc0 = grp * 64 + (lane & 15) * 4;   // first of this lane's four columns inside the query block
-    auto fetch_stat = [&](int b, int h, int it, float (&v)[4]) {
-      const float* base = stat_src + (static_cast<long long>(b) * H + h) * L;
+    auto stat_base = [&](int b, int h) { return stat_src + (static_cast<long long>(b) * H + h) * L; };
+    auto fetch_stat = [&](const float* base, int it, float (&v)[4]) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = __ldg(base + min(it * BQ + sc0 + j, L - 1));
     };
@@ -240,19 +257,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 
     // read this warp's 32 rows x 32 columns of a finished dQ tile and add them to the global accumulator (one TMA reduce per warp)
     const uint32_t my_box = sDQ + grp * TILE + quad * 32 * 128;
-    auto flush_dq = [&](int b, int h, int qb) {
+    // stage: TMEM -> registers -> staging box; issue (after a proxy fence + __syncwarp by the caller): one bulk reduction
+    auto stage_dq = [&]() {
       uint32_t r[32];
       tmem_ld32(tmem + DQ + lane_off + grp * 32, r);
-      tmem_wait_ld();
       if (lane == 0) tma_store_wait_read<0>();   // this warp's previous reduction has read its staging box
+      tmem_wait_ld();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         fb_sts_f4(my_box + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
+    };
+    auto issue_dq = [&](int b, int h, int qb) {
       if (lane == 0) {
         fb_tma_reduce_add_3d(&map_dq, my_box, h * HD + grp * 32, qb * BQ + quad * 32, b);
         tma_store_commit();
@@ -264,7 +281,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       int b, h, r0;
       decode(blockIdx.x, b, h, r0);
       float v[4];
-      fetch_stat(b, h, 0, v);
+      fetch_stat(stat_base(b, h), 0, v);
       deposit_stat(0, 0, v);
     }
     __syncwarp();
@@ -273,19 +290,21 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       decode(w, b, h, r0);
       const int g_row = r0 + row;
       FB_TRACE_ITEM((w - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x));
+      const float* cur_stat = stat_base(b, h);
+      const float* nxt_item_stat = cur_stat;
+      const bool more_items = w + static_cast<int>(gridDim.x) < total;
+      if (more_items) {
+        int nb, nh, nr0;
+        decode(w + gridDim.x, nb, nh, nr0);
+        nxt_item_stat = stat_base(nb, nh);
+      }
       for (int it = 0; it < niter; ++it, ++gi) {
         // statistics of the next query block (of this item, or the first block of the next item)
         float nxt_stat[4] = {0.f, 0.f, 0.f, 0.f};
-        bool has_next = true;
-        int nit = it + 1;
-        {
-          int nb = b, nh = h, nr0;
-          if (nit == niter) {
-            nit = 0;
-            if (w + static_cast<int>(gridDim.x) < total) decode(w + gridDim.x, nb, nh, nr0); else has_next = false;
-          }
-          if (has_next) fetch_stat(nb, nh, nit, nxt_stat);
-        }
+        const bool last = it + 1 == niter;
+        const bool has_next = !last || more_items;
+        const int nit = last ? 0 : it + 1;
+        if (has_next) fetch_stat(last ? nxt_item_stat : cur_stat, nit, nxt_stat);
         ATT_STAMP_T(0, it, 0, 128);
         const float* st_lse = wstat + (gi & 1) * 128;
         const float* st_delta = st_lse + 64;
@@ -310,12 +329,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
             const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c * 32 + 4 * i4);
             const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
             const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pv[4];
+            if (i4 < VMAE_FB_POLY) {   // MUFU delivers 16 ex2/clk/SM: a share of the exponentials goes to the FMA pipe
+              fb_exp2_poly2(fmaf(__uint_as_float(ts[c][4 * i4]), sl2, -lv[0]), fmaf(__uint_as_float(ts[c][4 * i4 + 1]), sl2, -lv[1]), pv[0], pv[1]);
+              fb_exp2_poly2(fmaf(__uint_as_float(ts[c][4 * i4 + 2]), sl2, -lv[2]), fmaf(__uint_as_float(ts[c][4 * i4 + 3]), sl2, -lv[3]), pv[2], pv[3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) pv[t] = fb_ex2(fmaf(__uint_as_float(ts[c][4 * i4 + t]), sl2, -lv[t]));
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int i = 4 * i4 + t;
-              const float p = fb_ex2(fmaf(__uint_as_float(ts[c][i]), sl2, -lv[t]));
-              ts[c][i] = __float_as_uint(p);
-              tp[c][i] = __float_as_uint(p * (__uint_as_float(tp[c][i]) - dv[t]));
+              ts[c][i] = __float_as_uint(pv[t]);
+              tp[c][i] = __float_as_uint(pv[t] * (__uint_as_float(tp[c][i]) - dv[t]));
             }
           }
         ATT_STAMP_T(0, it, 3, 128);
@@ -324,7 +350,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
           mbar_wait(acc_done, (gi - 1) & 1);
           tc_fence_after();
           ATT_STAMP_T(0, it, 4, 128);
-          flush_dq(b, h, it - 1);
+          stage_dq();   // its bulk reduction is issued behind the proxy fence that also publishes dS^T below
           ATT_STAMP_T(0, it, 5, 128);
         }
         // P^T half -> TMEM operand (32 packed columns), dS^T half -> shared-memory tile chunk `grp`
@@ -353,6 +379,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
+        if (it > 0) issue_dq(b, h, it - 1);
         ATT_STAMP_T(0, it, 7, 128);
         if (has_next) deposit_stat(gi + 1, nit, nxt_stat);   // the other buffer: this warp finished reading it an iteration ago
         __syncwarp();
@@ -362,7 +389,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       mbar_wait(acc_done, (gi - 1) & 1);
       tc_fence_after();
       ATT_STAMP_T(0, niter, 1, 128);
-      flush_dq(b, h, niter - 1);
+      stage_dq();
+      fence_proxy_async_smem();
+      __syncwarp();
+      issue_dq(b, h, niter - 1);
       ATT_STAMP_T(0, niter, 2, 128);
       const long long row_off = (static_cast<long long>(b) * L + g_row) * (3 * H * HD);
       uint32_t ra[2][32];   // group 0: dK, group 1: dV (2 x 32 columns): both loads in flight, one wait
