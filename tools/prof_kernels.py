@@ -35,7 +35,8 @@ for _ in range(2):
     y, mean, rstd = ops.layernorm_fwd(xf, gm, bt)                                  # 7 LN fwd
     ops.layernorm_bwd(x, xf, gm, mean, rstd, dx_resid=xf, want_bf16=True)          # 8 LN bwd
     out, lse = ops.attn_fwd(qkv, B, Lq, H, hd)                                     # 9 attention fwd
-    ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)                                # 10-12 delta, dQ, dK/dV
+    ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)                                # delta, single-pass backward, dQ convert
+    ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, fused=False)                   # delta, dQ, dK/dV (two-kernel form)
     ops.masked_mse(pred, clip, mask, 2, 16, 1)                                     # 13-14 loss (+ finalize)
 torch.cuda.synchronize()
 print("done")
