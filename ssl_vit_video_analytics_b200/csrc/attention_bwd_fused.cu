@@ -24,8 +24,18 @@ namespace vmae {
 namespace fb {
 constexpr int HD = 64;
 constexpr int BQ = 128;                    // query rows per block (columns of the score tiles)
-constexpr int THREADS = 384;               // warpgroup 0: TMA warp, UMMA warp (+2 idle); warpgroups 1, 2: 8 row warps
-constexpr int CTRL_REGS = 64, ROW_REGS = 216;   // setmaxnreg: 128 x 64 + 256 x 216 = 63488 <= 384 x 168 registers
+// G = number of row warpgroups (4 warps each): a row thread owns one key row and 128 / G query columns of every score tile.
+template <int G>
+struct Cfg {
+  static_assert(G == 2 || G == 4, "two or four row warpgroups");
+  static constexpr int THREADS = 128 + G * 128;     // warpgroup 0: TMA warp, UMMA warp (+2 idle); then G row warpgroups
+  static constexpr int COLS = 128 / G;              // query columns per row thread
+  static constexpr int NCH = COLS / 32;             // 32-column register chunks
+  static constexpr int DQC = 64 / G;                // dQ-tile columns read out per row thread
+  // setmaxnreg budgets: G = 2: 128 x 64 + 256 x 216 <= 384 x 168; G = 4: 128 x 56 + 512 x 104 <= 640 x 96
+  static constexpr int CTRL_REGS = (G == 2) ? 64 : 56;
+  static constexpr int ROW_REGS = (G == 2) ? 216 : 104;
+};
 constexpr int NS = 3;                      // Q/dO ring depth
 constexpr int TILE = 128 * HD * 2;         // one [128 x 64] bf16 operand tile: 16 KB
 constexpr int OFF_K = 0;
@@ -33,7 +43,7 @@ constexpr int OFF_V = OFF_K + TILE;
 constexpr int OFF_Y = OFF_V + TILE;        // [NS][2] tiles: Q_i, dO_i
 constexpr int OFF_E = OFF_Y + NS * 2 * TILE;       // dS^T: [128 key rows x 128 queries] bf16 = two 64-column SW128 chunks (32 KB)
 constexpr int OFF_DQ = OFF_E + 2 * TILE;           // dQ staging: two [128 x 32] fp32 SW128 boxes (32 KB)
-constexpr int OFF_STAT = OFF_DQ + 2 * TILE;        // per row warp: [2 buffers][lse*log2e (64) | delta (64)] fp32 = 1 KB; 8 warps
+constexpr int OFF_STAT = OFF_DQ + 2 * TILE;        // per row warp: [2 buffers][lse*log2e (COLS) | delta (COLS)] fp32; 8 KB in total
 constexpr int OFF_BAR = OFF_STAT + 8 * 2 * 128 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
@@ -61,6 +71,9 @@ __device__ __forceinline__ void fb_exp2_poly2(float x0, float x1, float& y0, flo
   y0 = __uint_as_float(__float_as_uint(pl) + (__float_as_uint(tl) << 23));
   y1 = __uint_as_float(__float_as_uint(ph) + (__float_as_uint(th) << 23));
 }
+#ifndef VMAE_FB_GROUPS
+#define VMAE_FB_GROUPS 2   // row warpgroups of the single-pass backward (2 or 4; 4 measured slower: 1377 vs 1008 us, register-starved at 104/thread)
+#endif
 #ifndef VMAE_FB_POLY
 #define VMAE_FB_POLY 0   // of every 8 column quads, this many take the polynomial exp2 (measured: no gain here, the phase is not MUFU-bound)
 #endif
@@ -85,11 +98,14 @@ __device__ __forceinline__ void fb_tma_reduce_add_3d(const CUtensorMap* m, uint3
 // Persistent: grid = #SMs; a CTA walks work items w = (b, h, key tile) with stride gridDim.x (consecutive items share (b, h),
 // so co-running CTAs stream the same Q_i / dO_i blocks out of L2). TMEM is allocated once, the mbarrier phases run on across
 // items, and the next item's K/V load overlaps the current item's dK/dV read-out.
-__global__ void __launch_bounds__(fb::THREADS, 1)
+template <int G>
+__global__ void __launch_bounds__(fb::Cfg<G>::THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                       const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ lse, const float* __restrict__ delta,
                       __nv_bfloat16* __restrict__ dqkv, int L, int H, int B, float scale) {
   using namespace fb;
+  using C = Cfg<G>;
+  constexpr int COLS = C::COLS, NCH = C::NCH, DQC = C::DQC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if (threadIdx.x == 0 && (sbase & 1023u) != 0) { printf("vmae attention: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
@@ -126,8 +142,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     tma_prefetch_desc(&map_dq);
     mbar_init(res_full, 1);
     mbar_init(t_full, 1);
-    mbar_init(t_free, 8);
-    mbar_init(p_ready, 8);
+    mbar_init(t_free, 4 * G);
+    mbar_init(p_ready, 4 * G);
     mbar_init(acc_done, 1);
     mbar_init(kv_free, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 1); }
@@ -140,7 +156,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   const uint32_t tmem = *tmem_ptr_gen;
 
   if (warp < 4) {
-    setmaxnreg_dec<CTRL_REGS>();
+    setmaxnreg_dec<C::CTRL_REGS>();
   if (warp == 0) {
     if (elect_one()) {   // TMA producer
       uint32_t gi = 0, item_n = 0;
@@ -165,24 +181,23 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, BQ, 0, 0);    // T = A(K-major) x B(K-major), N = 128
       constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);    // acc += A(K-major | TMEM) x B(MN-major), N = 64
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 1, 1);    // dQ = A(MN-major) x B(MN-major)
-      const uint64_t dK_k = umma_smem_desc(sK, 0, 1024, 128);         // K as K-major A (and, advanced by rows, as MN-major B)
-      const uint64_t dV_k = umma_smem_desc(sV, 0, 1024, 128);
-      uint64_t dQ_[NS], dO_[NS];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        dQ_[s] = umma_smem_desc(sY(s, 0), 0, 1024, 128);
-        dO_[s] = umma_smem_desc(sY(s, 1), 0, 1024, 128);
-      }
-      const uint64_t dE_k = umma_smem_desc(sE, 0, 1024, 128);             // dS^T, K-major: 64-query chunks 16 KB apart
-      const uint64_t dE_mn = umma_smem_desc(sE, 128 * 128, 1024, 128);    // dS, MN-major: LBO = stride between the two 64-wide M chunks
+      // every operand tile sits at a fixed offset from the 1024-aligned smem base, so one descriptor (two registers) serves all
+      // of them: only the 14-bit start-address field (bytes >> 4) differs
+      const uint64_t d0 = umma_smem_desc(sbase, 0, 1024, 128);
+      const uint64_t dK_k = d0 + (OFF_K >> 4);                        // K as K-major A (and, advanced by rows, as MN-major B)
+      const uint64_t dV_k = d0 + (OFF_V >> 4);
+      auto dQ_ = [&](int s) { return d0 + ((OFF_Y + (s * 2) * TILE) >> 4); };
+      auto dO_ = [&](int s) { return d0 + ((OFF_Y + (s * 2 + 1) * TILE) >> 4); };
+      const uint64_t dE_k = d0 + (OFF_E >> 4);                                                   // dS^T, K-major: 64-query chunks 16 KB apart
+      const uint64_t dE_mn = umma_smem_desc(sbase, 128 * 128, 1024, 128) + (OFF_E >> 4);         // dS, MN-major: LBO = stride between the two 64-wide M chunks
       auto issue_t = [&](uint32_t g) {
         const int s = g % NS;
         mbar_wait(st_full(s), (g / NS) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T0, dK_k + 2 * k, dQ_[s] + 2 * k, idesc_t, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T0, dK_k + 2 * k, dQ_(s) + 2 * k, idesc_t, k > 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T1, dV_k + 2 * k, dO_[s] + 2 * k, idesc_t, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T1, dV_k + 2 * k, dO_(s) + 2 * k, idesc_t, k > 0);
         umma_commit(t_full);
       };
       uint32_t gi = 0, item_n = 0;
@@ -207,10 +222,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
           ATT_STAMP(1, it, 3);
 #pragma unroll
           for (int kk = 0; kk < BQ / 16; ++kk)   // dV += P^T dO_i  (contraction over the 128 queries)
-            umma_bf16_ts(tmem + DV, tmem + TP + kk * 8, dO_[s] + kk * 128, idesc_a, (it > 0 || kk > 0));
+            umma_bf16_ts(tmem + DV, tmem + TP + kk * 8, dO_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < BQ / 16; ++kk)   // dK += dS^T Q_i
-            umma_bf16(tmem + DK, dE_k + (kk >> 2) * 1024 + 2 * (kk & 3), dQ_[s] + kk * 128, idesc_a, (it > 0 || kk > 0));
+            umma_bf16(tmem + DK, dE_k + (kk >> 2) * 1024 + 2 * (kk & 3), dQ_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < 128 / 16; ++kk)  // dQ_i = dS K      (contraction over the 128 keys of this CTA)
             umma_bf16(tmem + DQ, dE_mn + kk * 128, dK_k + kk * 128, idesc_q, kk > 0);
@@ -223,55 +238,63 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     }
   }
   } else {
-    setmaxnreg_inc<ROW_REGS>();
-    // Eight row warps = two groups of four: a thread owns key row `row` (= TMEM lane) and the 64 query columns of its group's half
-    // of every score tile, so each sub-partition has two row warps whose phases overlap. Group g also owns columns
-    // [32g, 32g+32) of each dQ tile and, in the item tail, dK (g = 0) or dV (g = 1).
+    setmaxnreg_inc<C::ROW_REGS>();
+    // 4 * G row warps = G groups of four: a thread owns key row `row` (= TMEM lane) and the COLS query columns of its group of
+    // every score tile, so each SM sub-partition has G row warps whose phases overlap. Group g also owns DQC columns of each
+    // dQ tile and, in the item tail, COLS of the 128 dK | dV accumulator columns.
     const int grp = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int tid = threadIdx.x - 128;      // 0..255 among the row threads
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float sl2 = scale * LOG2E_F;
-    // Column statistics (lse_i, delta_i) of this group's 64 query columns live in a warp-private, double-buffered shared array:
-    // lanes 0..15 fetch four lse values each, lanes 16..31 four delta values, so the row warps never meet at a CTA barrier.
-    // The loads are unconditional (clamped index) and nothing touches their results until they are deposited one iteration
-    // later: a select or multiply right behind the load would stall the warp for the full DRAM latency.
-    float* wstat = stat + (warp - 4) * 2 * 128;
-    const float* stat_src = (lane < 16) ? lse : delta;
-    const int sc0 = grp * 64 + (lane & 15) * 4;   // first of this lane's four columns inside the query block
+    // Column statistics (lse_i, delta_i) of this group's query columns live in a warp-private, double-buffered shared array:
+    // the first COLS/4 lanes fetch four lse values each, the next COLS/4 lanes four delta values, so the row warps never meet
+    // at a CTA barrier. The loads are unconditional (clamped index) and nothing touches their results until they are deposited
+    // one iteration later: a select or multiply right behind the load would stall the warp for the full DRAM latency.
+    constexpr int NL = COLS / 4;
+    float* wstat = stat + (warp - 4) * 2 * (2 * COLS);
+    const bool stat_lane = lane < 2 * NL;
+    const float* stat_src = (lane < NL) ? lse : delta;
+    const int sc0 = grp * COLS + (lane % NL) * 4;   // first of this lane's four columns inside the query block
     auto stat_base = [&](int b, int h) { return stat_src + (static_cast<long long>(b) * H + h) * L; };
     auto fetch_stat = [&](const float* base, int it, float (&v)[4]) {
+      if (stat_lane) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = __ldg(base + min(it * BQ + sc0 + j, L - 1));
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(base + min(it * BQ + sc0 + j, L - 1));
+      }
     };
     auto deposit_stat = [&](uint32_t g, int it, const float (&v)[4]) {   // lse * log2(e), +inf past the end (p == 0); delta, 0 past the end
-      float o[4];
+      if (stat_lane) {
+        float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool in = it * BQ + sc0 + j < L;
-        o[j] = (lane < 16) ? (in ? v[j] * LOG2E_F : INFINITY) : (in ? v[j] : 0.f);
+        for (int j = 0; j < 4; ++j) {
+          const bool in = it * BQ + sc0 + j < L;
+          o[j] = (lane < NL) ? (in ? v[j] * LOG2E_F : INFINITY) : (in ? v[j] : 0.f);
+        }
+        *reinterpret_cast<float4*>(wstat + (g & 1) * (2 * COLS) + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);   // delta lanes land in [COLS, 2 COLS)
       }
-      *reinterpret_cast<float4*>(wstat + (g & 1) * 128 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);   // lanes 16..31 land in [64, 128)
     };
 
-    // read this warp's 32 rows x 32 columns of a finished dQ tile and add them to the global accumulator (one TMA reduce per warp)
-    const uint32_t my_box = sDQ + grp * TILE + quad * 32 * 128;
-    // stage: TMEM -> registers -> staging box; issue (after a proxy fence + __syncwarp by the caller): one bulk reduction
+    // this warp's 32 rows x DQC columns of a finished dQ tile. stage: TMEM -> registers -> staging box; issue (after a proxy
+    // fence + __syncwarp by the caller): one bulk reduction into the global accumulator
+    const uint32_t my_box = sDQ + (warp - 4) * (32 * DQC * 4);
     auto stage_dq = [&]() {
-      uint32_t r[32];
-      tmem_ld32(tmem + DQ + lane_off + grp * 32, r);
+      uint32_t r[DQC];
+      if (DQC == 32) tmem_ld32(tmem + DQ + lane_off + grp * DQC, reinterpret_cast<uint32_t(&)[32]>(r));
+      else tmem_ld16(tmem + DQ + lane_off + grp * DQC, reinterpret_cast<uint32_t(&)[16]>(r));
       if (lane == 0) tma_store_wait_read<0>();   // this warp's previous reduction has read its staging box
       tmem_wait_ld();
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        fb_sts_f4(my_box + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      for (int j = 0; j < DQC / 4; ++j) {
+        // 128-byte rows use the 128B TMA swizzle; 64-byte rows (G = 4) are stored linearly
+        const uint32_t addr = (DQC == 32) ? my_box + lane * 128 + ((j ^ (lane & 7)) << 4) : my_box + lane * 64 + (j << 4);
+        fb_sts_f4(addr, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
     };
     auto issue_dq = [&](int b, int h, int qb) {
       if (lane == 0) {
-        fb_tma_reduce_add_3d(&map_dq, my_box, h * HD + grp * 32, qb * BQ + quad * 32, b);
+        fb_tma_reduce_add_3d(&map_dq, my_box, h * HD + grp * DQC, qb * BQ + quad * 32, b);
         tma_store_commit();
       }
     };
@@ -306,23 +329,23 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
         const int nit = last ? 0 : it + 1;
         if (has_next) fetch_stat(last ? nxt_item_stat : cur_stat, nit, nxt_stat);
         ATT_STAMP_T(0, it, 0, 128);
-        const float* st_lse = wstat + (gi & 1) * 128;
-        const float* st_delta = st_lse + 64;
+        const float* st_lse = wstat + (gi & 1) * (2 * COLS);
+        const float* st_delta = st_lse + COLS;
         ATT_STAMP_T(0, it, 1, 128);
         mbar_wait(t_full, gi & 1);
         tc_fence_after();
         ATT_STAMP_T(0, it, 2, 128);
-        uint32_t ts[2][32], tp[2][32];   // this group's 64 columns of T0 (scores) and T1 (dP) of this key row
+        uint32_t ts[NCH][32], tp[NCH][32];   // this group's columns of T0 (scores) and T1 (dP) of this key row
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tmem + T0 + lane_off + grp * 64 + c * 32, ts[c]);
-          tmem_ld32(tmem + T1 + lane_off + grp * 64 + c * 32, tp[c]);
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld32(tmem + T0 + lane_off + grp * COLS + c * 32, ts[c]);
+          tmem_ld32(tmem + T1 + lane_off + grp * COLS + c * 32, tp[c]);
         }
         tmem_wait_ld();
         tc_fence_before();
         if (lane == 0) mbar_arrive(t_free);   // the tiles are in registers: T(it+1) is computed underneath the element-wise phase
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < NCH; ++c)
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
             const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c * 32 + 4 * i4);
@@ -353,20 +376,21 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
           stage_dq();   // its bulk reduction is issued behind the proxy fence that also publishes dS^T below
           ATT_STAMP_T(0, it, 5, 128);
         }
-        // P^T half -> TMEM operand (32 packed columns), dS^T half -> shared-memory tile chunk `grp`
+        // P^T columns -> TMEM operand (packed pairs), dS^T columns -> shared-memory tile (64-column SW128 chunks)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           uint32_t u[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) u[i] = fb_pack(__uint_as_float(ts[c][2 * i]), __uint_as_float(ts[c][2 * i + 1]));
-          tmem_st16(tmem + TP + lane_off + grp * 32 + c * 16, u);
+          tmem_st16(tmem + TP + lane_off + grp * (COLS / 2) + c * 16, u);
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t row_base = sE + grp * TILE + row * 128;
+        for (int c = 0; c < NCH; ++c) {
+          const int col = grp * COLS + c * 32;   // first of these 32 query columns inside the block
+          const uint32_t row_base = sE + (col >> 6) * TILE + row * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t addr = row_base + ((((c * 32) >> 3) + i) ^ (row & 7)) * 16;
+            const uint32_t addr = row_base + ((((col & 63) >> 3) + i) ^ (row & 7)) * 16;
             fb_sts_u4(addr, fb_pack(__uint_as_float(tp[c][8 * i]), __uint_as_float(tp[c][8 * i + 1])),
                       fb_pack(__uint_as_float(tp[c][8 * i + 2]), __uint_as_float(tp[c][8 * i + 3])),
                       fb_pack(__uint_as_float(tp[c][8 * i + 4]), __uint_as_float(tp[c][8 * i + 5])),
@@ -395,15 +419,20 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       issue_dq(b, h, niter - 1);
       ATT_STAMP_T(0, niter, 2, 128);
       const long long row_off = (static_cast<long long>(b) * L + g_row) * (3 * H * HD);
-      uint32_t ra[2][32];   // group 0: dK, group 1: dV (2 x 32 columns): both loads in flight, one wait
+      // this group's COLS of the 128 accumulator columns [dK (64) | dV (64)]: all loads in flight, one wait
+      constexpr int ACC_A = 0;
+      const int acol = grp * COLS;                     // 0..127 over dK | dV
+      const int part = 1 + (acol >> 6);                // 1 = k slot, 2 = v slot of dqkv
+      const uint32_t tA = tmem + ((acol >> 6) == ACC_A ? DK : DV) + (acol & 63);
+      uint32_t ra[NCH][32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld32(tmem + (grp == 0 ? DK : DV) + lane_off + c * 32, ra[c]);
+      for (int c = 0; c < NCH; ++c) tmem_ld32(tA + lane_off + c * 32, ra[c]);
       tmem_wait_ld();
       if (g_row < L) {
-        const float f = (grp == 0) ? scale : 1.0f;   // dS was accumulated without the softmax scale
+        const float f = (part == 1) ? scale : 1.0f;   // dS was accumulated without the softmax scale
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          __nv_bfloat16* dst = dqkv + row_off + ((grp + 1) * H + h) * HD + c * 32;
+        for (int c = 0; c < NCH; ++c) {
+          __nv_bfloat16* dst = dqkv + row_off + (part * H + h) * HD + (acol & 63) + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 pk;
@@ -464,18 +493,19 @@ int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, con
     int rc = make_tmap_bf16(&m_do, dout, 3, dims, str, box, 128);
     if (rc) return rc;
   }
+  constexpr int G = VMAE_FB_GROUPS;
   {
     const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
     const uint64_t str[2] = {(uint64_t)H * HD * 4, (uint64_t)L * H * HD * 4};
-    const uint32_t box[3] = {32, 32, 1};   // one reduction per row warp: 32 query rows x 32 head-dim columns
-    int rc = make_tmap(&m_dq, dq_accum, VMAE_DTYPE_F32, 3, dims, str, box, 128);
+    const uint32_t box[3] = {(uint32_t)Cfg<G>::DQC, 32, 1};   // one reduction per row warp: 32 query rows x DQC head-dim columns
+    int rc = make_tmap(&m_dq, dq_accum, VMAE_DTYPE_F32, 3, dims, str, box, Cfg<G>::DQC * 4 == 128 ? 128 : 0);
     if (rc) return rc;
   }
   VMAE_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * L * H * HD * sizeof(float), stream));
-  VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const long long items = (long long)B * H * ((L + 127) / 128);
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_bwd_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale);
+  attn_bwd_fused_kernel<G><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale);
   VMAE_LAUNCH_CHECK();
   const long long rows = (long long)B * L;
   long long g = (rows * (H * HD / 4) + 255) / 256;
