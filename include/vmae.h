@@ -75,7 +75,7 @@ int vmae_linear_wgrad(const void* dy, long long ld_dy, const void* x, long long 
 int vmae_attn_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, float p_drop,
                   unsigned long long seed, void* stream);
 /* dqkv: bf16 [B, L, 3, H, hd]; delta: fp32 workspace [B, H, L] (rowsum(dO*O), written by the call).
- * dq_accum: optional fp32 workspace [B, L, H*hd]. When given (and hd == 64, p_drop == 0) the single-pass backward runs: one
+ * dq_accum: optional fp32 workspace [B, L, H*hd]. When given (and hd == 64) the single-pass backward runs: one
  * kernel computes dK, dV and the per-block partial dQ (5 GEMM units, one exponential per score) and reduces dQ into this
  * buffer through L2 (TMA reduce-add; the summation order of dQ is then not deterministic); NULL selects the two-kernel form. */
 int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum,

@@ -35,22 +35,7 @@ __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2; exp2
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Attention-probability dropout (nn.MultiheadAttention(dropout=p), mae_vit_adapter.py:40-47): a stateless hash of
-// (seed, batch*head, query, key pair) gives two 16-bit uniforms, so the forward and both backward kernels regenerate the same
-// keep mask without storing it. Element (q, k) is dropped when its half of the word is below thr = round(p * 65536).
-struct AttnDrop {
-  uint32_t seed_lo, seed_hi, thr;
-  float rp;   // 1 / (1 - thr / 65536)
-};
-__device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-constexpr uint32_t DROP_CQ = 0x9E3779B1u, DROP_CK = 0x85EBCA77u;
-// word for query row id `rid` (= (b*H + h)*L + q) and key pair kp (= k >> 1): low half -> even k, high half -> odd k
-__device__ __forceinline__ uint32_t drop_word(const AttnDrop& d, uint32_t rid, uint32_t kp) {
-  return drop_mix32(rid * DROP_CQ + kp * DROP_CK + d.seed_lo) ^ d.seed_hi;
-}
+#include "att_drop.cuh"
 // 2^x for a pair of lanes on the FMA pipe (the MUFU pipe delivers only 16 ex2 per clock per SM and is the forward kernel's
 // first bound): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial for 2^f (relative error 7.5e-5,
 // far below the bf16 rounding of P), exponent added as an integer. Arguments are clamped at -125 (result ~ 0).
@@ -705,14 +690,7 @@ static int make_map_rows(CUtensorMap* m, const void* base, int B, int L, int wid
   return make_tmap_bf16(m, base, 3, dims, str, box, hd * 2);
 }
 
-static AttnDrop make_drop(float p_drop, unsigned long long seed) {
-  AttnDrop d;
-  d.seed_lo = static_cast<uint32_t>(seed);
-  d.seed_hi = static_cast<uint32_t>(seed >> 32);
-  d.thr = static_cast<uint32_t>(p_drop * 65536.0f + 0.5f);
-  d.rp = 65536.0f / (65536.0f - static_cast<float>(d.thr));
-  return d;
-}
+static AttnDrop make_drop(float p_drop, unsigned long long seed) { return make_attn_drop(p_drop, seed); }
 
 template <int HD, int BKV>
 static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, float p_drop, unsigned long long seed,
@@ -813,7 +791,7 @@ extern "C" int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_d
 
 namespace vmae {
 int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* dq_accum, int B, int L, int H,
-                        float scale, cudaStream_t stream);   // attention_bwd_fused.cu
+                        float scale, float p_drop, unsigned long long seed, cudaStream_t stream);   // attention_bwd_fused.cu
 }
 
 extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, float* dq_accum, void* dqkv,
@@ -832,8 +810,8 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
     attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
     VMAE_LAUNCH_CHECK();
     // single-pass kernel (5 GEMM units, one exponential per score, dQ reduced through L2) when the caller provides the fp32
-    // dQ accumulator; the two-kernel form otherwise and whenever dropout is active
-    if (dq_accum != nullptr && p_drop == 0.f) return attn_bwd_fused_hd64(qkv, dout, lse, delta, dqkv, dq_accum, B, L, H, scale, s);
+    // dQ accumulator; the two-kernel form otherwise
+    if (dq_accum != nullptr) return attn_bwd_fused_hd64(qkv, dout, lse, delta, dqkv, dq_accum, B, L, H, scale, p_drop, seed, s);
     rc = launch_bwd<64, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
     if (rc) return rc;
     return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);

@@ -20,6 +20,7 @@
 namespace vmae {
 
 #include "att_trace.cuh"
+#include "att_drop.cuh"
 
 namespace fb {
 constexpr int HD = 64;
@@ -98,11 +99,11 @@ __device__ __forceinline__ void fb_tma_reduce_add_3d(const CUtensorMap* m, uint3
 // Persistent: grid = #SMs; a CTA walks work items w = (b, h, key tile) with stride gridDim.x (consecutive items share (b, h),
 // so co-running CTAs stream the same Q_i / dO_i blocks out of L2). TMEM is allocated once, the mbarrier phases run on across
 // items, and the next item's K/V load overlaps the current item's dK/dV read-out.
-template <int G>
+template <int G, bool DROP>
 __global__ void __launch_bounds__(fb::Cfg<G>::THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                       const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ lse, const float* __restrict__ delta,
-                      __nv_bfloat16* __restrict__ dqkv, int L, int H, int B, float scale) {
+                      __nv_bfloat16* __restrict__ dqkv, int L, int H, int B, float scale, const AttnDrop drop) {
   using namespace fb;
   using C = Cfg<G>;
   constexpr int COLS = C::COLS, NCH = C::NCH, DQC = C::DQC;
@@ -312,6 +313,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       int b, h, r0;
       decode(w, b, h, r0);
       const int g_row = r0 + row;
+      const uint32_t drop_base = static_cast<uint32_t>(g_row >> 1) * DROP_CK + drop.seed_lo;
       FB_TRACE_ITEM((w - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x));
       const float* cur_stat = stat_base(b, h);
       const float* nxt_item_stat = cur_stat;
@@ -363,8 +365,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int i = 4 * i4 + t;
-              ts[c][i] = __float_as_uint(pv[t]);
-              tp[c][i] = __float_as_uint(pv[t] * (__uint_as_float(tp[c][i]) - dv[t]));
+              float dp = __uint_as_float(tp[c][i]);
+              float pd = pv[t];   // the dropped probability (scaled by 1/(1-p) when dV is written out)
+              if (DROP) {   // same keep mask as the forward kernel: hash of (seed, query row, key pair); this thread owns key g_row
+                const uint32_t rid = static_cast<uint32_t>((b * H + h) * L + it * BQ + grp * COLS + c * 32 + i);
+                const uint32_t wd = drop_mix32(rid * DROP_CQ + drop_base) ^ drop.seed_hi;
+                const bool dropped = (((g_row & 1) ? (wd >> 16) : (wd & 0xffffu)) < drop.thr);
+                dp = dropped ? 0.f : dp * drop.rp;
+                pd = dropped ? 0.f : pd;
+              }
+              ts[c][i] = __float_as_uint(pd);
+              tp[c][i] = __float_as_uint(pv[t] * (dp - dv[t]));
             }
           }
         ATT_STAMP_T(0, it, 3, 128);
@@ -429,7 +440,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       for (int c = 0; c < NCH; ++c) tmem_ld32(tA + lane_off + c * 32, ra[c]);
       tmem_wait_ld();
       if (g_row < L) {
-        const float f = (part == 1) ? scale : 1.0f;   // dS was accumulated without the softmax scale
+        const float f = (part == 1) ? scale : (DROP ? drop.rp : 1.0f);   // dS was accumulated without the softmax scale, P^T without 1/(1-p)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           __nv_bfloat16* dst = dqkv + row_off + (part * H + h) * HD + (acol & 63) + c * 32;
@@ -476,7 +487,7 @@ int att_trace_read_fused(long long* host) { return att_trace_read_tu(host); }
 
 // Returns 0 on success, <0 on error. dq_accum: fp32 [B, L, H*64] workspace (zeroed here).
 int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* dq_accum, int B, int L, int H,
-                        float scale, cudaStream_t stream) {
+                        float scale, float p_drop, unsigned long long seed, cudaStream_t stream) {
   using namespace fb;
   CUtensorMap m_qkv, m_do, m_dq;
   {
@@ -502,10 +513,16 @@ int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, con
     if (rc) return rc;
   }
   VMAE_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * L * H * HD * sizeof(float), stream));
-  VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const long long items = (long long)B * H * ((L + 127) / 128);
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_bwd_fused_kernel<G><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale);
+  const AttnDrop drop = make_attn_drop(p_drop, seed);
+  if (drop.thr > 0) {
+    VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attn_bwd_fused_kernel<G, true><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop);
+  } else {
+    VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attn_bwd_fused_kernel<G, false><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop);
+  }
   VMAE_LAUNCH_CHECK();
   const long long rows = (long long)B * L;
   long long g = (rows * (H * HD / 4) + 255) / 256;

@@ -279,7 +279,7 @@ def attn_fwd(qkv, B, Lq, H, hd, p_drop=0.0, seed=0):
     return out, lse
 
 
-ATTN_BWD_FUSED = True   # single-pass backward (head_dim 64, no dropout); False forces the two-kernel form
+ATTN_BWD_FUSED = True   # single-pass backward (head_dim 64); False forces the two-kernel form
 ATTN_BWD_FUSED_MIN_L = 384
 
 
@@ -288,7 +288,7 @@ def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, p_drop=0.0, seed=0, fused=None):
     delta = torch.empty((B, H, Lq), device=qkv.device, dtype=F32)
     # measured: the single-pass kernel wins from a few hundred tokens up (L=1568: 1059 vs 1322 us); short sequences (L=160) are
     # setup-dominated and stay on the two-kernel form
-    use_fused = ((ATTN_BWD_FUSED and Lq >= ATTN_BWD_FUSED_MIN_L) if fused is None else fused) and hd == 64 and p_drop == 0.0
+    use_fused = ((ATTN_BWD_FUSED and Lq >= ATTN_BWD_FUSED_MIN_L) if fused is None else fused) and hd == 64
     dq_acc = torch.empty((B * Lq, H * hd), device=qkv.device, dtype=F32) if use_fused else None
     L.check(_run("attn_bwd", 10.0 * B * H * Lq * Lq * hd, lambda: L.load().vmae_attn_bwd(
         _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dq_acc), _p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), float(p_drop), int(seed),

@@ -392,15 +392,16 @@ def test_flash_attention_dropout_fwd_bwd(env, B, Lq, H, hd):
     keep = ops.attn_dropout_mask(B, Lq, H, p, seed, dev).float()                   # [B, H, L, L]
     assert abs(float(keep.mean()) - (1 - p_eff)) < 0.01
     out, lse = ops.attn_fwd(qkv.view(B * Lq, -1), B, Lq, H, hd, p, seed)
-    dqkv = ops.attn_bwd(qkv.view(B * Lq, -1), out, dout.view(B * Lq, -1), lse, B, Lq, H, hd, p, seed).view(B, Lq, 3, H, hd)
     q32 = qkv.float().requires_grad_(True)
     q, k, v = [q32[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
     prob = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
     ref = ((prob * keep / (1 - p_eff)) @ v).permute(0, 2, 1, 3).reshape(B, Lq, H * hd)
     ref.backward(dout.float())
     assert relerr(out.view(B, Lq, -1), ref) < BF16_TOL
-    for i, name in enumerate("qkv"):
-        assert relerr(dqkv[:, :, i], q32.grad[:, :, i]) < 2 * BF16_TOL, name
+    for fused in ([False, True] if hd == 64 else [False]):   # two-kernel form and single-pass kernel regenerate the same mask
+        dqkv = ops.attn_bwd(qkv.view(B * Lq, -1), out, dout.view(B * Lq, -1), lse, B, Lq, H, hd, p, seed, fused=fused).view(B, Lq, 3, H, hd)
+        for i, name in enumerate("qkv"):
+            assert relerr(dqkv[:, :, i], q32.grad[:, :, i]) < 2 * BF16_TOL, (name, fused)
     out0, _ = ops.attn_fwd(qkv.view(B * Lq, -1), B, Lq, H, hd)                      # p = 0 path untouched
     assert relerr(out0.view(B, Lq, -1), (prob @ v).permute(0, 2, 1, 3).reshape(B, Lq, H * hd)) < BF16_TOL
 
