@@ -479,7 +479,9 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
                            float* dx_out, void* dx_out_bf16, float* dgamma, float* dbeta, long long rows, int cols, cudaStream_t s) {
   const int nv = (cols + 127) / 128;
   long long g = (rows + EW_WARPS - 1) / EW_WARPS;
-  const long long cap = (long long)num_sms() * 8;
+  // one resident wave (2 CTAs per SM at 128 registers): every CTA ends with 2 * cols atomics on the same dgamma / dbeta
+  // addresses, so extra waves only add contention (the 10240-row encoder launches were atomics-bound at 8 waves: 20 -> 9 us)
+  const long long cap = (long long)num_sms() * 2;
   const int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
   const size_t smem = (size_t)EW_WARPS * 2 * cols * sizeof(float);
 #define LN_CASE(NV)                                                                                                      \

@@ -8,7 +8,7 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from ssl_vit_video_analytics_b200 import _lib as L  # noqa: E402
+from ssl_vit_video_analytics_b200 import _lib as L, ops  # noqa: E402
 
 lib = C.CDLL(str(L.LIB_PATH))
 lib.vmae_gemm_bf16.argtypes = L.SIGNATURES["vmae_gemm_bf16"]
@@ -112,7 +112,7 @@ def _time(fn, iters=10):
 def mode_perf():
     g = torch.Generator(device="cuda").manual_seed(3)
     peak = 1644.1
-    M = 100352
+    M = int(sys.argv[2]) if len(sys.argv) > 2 else 100352   # 100352 = decoder rows (64 x 1568); 10240 = encoder rows (64 x 160)
     for (N, K, tag) in [(1536, 384, "fc1"), (384, 1536, "fc2"), (1152, 384, "qkv"), (384, 384, "proj")]:
         x = torch.randn(M, K, device=dev, generator=g).bfloat16()
         w = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
@@ -134,6 +134,7 @@ def mode_perf():
         dx = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
         rows.append(("dgrad", _time(lambda: gemm(dy, N, 0, w, K, 1, M, K, N, out=dx))))
         dw = torch.zeros(N, K, device=dev, dtype=torch.float32)
+        rows.append(("wgrad auto", _time(lambda: ops.linear_wgrad(dy, x))))
         for ks in (4, 12, 24):
             rows.append((f"wgrad ks={ks}", _time(lambda: gemm(dy, N, 1, x, K, 1, N, K, M, out=dw, out_fp32=True, accumulate=True, k_splits=ks))))
         print(f"perf {tag} M={M} N={N} K={K}: " + " | ".join(f"{n} {ms*1e3:.0f}us {fl/ms/1e9:.0f}TF" for n, ms in rows), flush=True)

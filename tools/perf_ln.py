@@ -39,3 +39,9 @@ print(f"ln bwd  (dy bf16, x f32, resid f32 -> dx f32 + bf16): {t:.1f} us  {b / t
 t = timeit(lambda: ops.layernorm_bwd(dy, x, gm, mean, rstd, dx_resid=None, want_bf16=False))
 b = rows * cols * (2 + 4 + 4)
 print(f"ln bwd  (dy bf16, x f32 -> dx f32): {t:.1f} us  {b / t / 1e3:.0f} GB/s")
+rows2 = 64 * 160
+x2 = torch.randn(rows2, cols, device=dev)
+dy2 = torch.randn(rows2, cols, device=dev).bfloat16()
+y2, m2, r2 = ops.layernorm_fwd(x2, gm, bt)
+print(f"encoder size ({rows2} rows): fwd {timeit(lambda: ops.layernorm_fwd(x2, gm, bt)):.1f} us, "
+      f"bwd {timeit(lambda: ops.layernorm_bwd(dy2, x2, gm, m2, r2, dx_resid=x2, want_bf16=True)):.1f} us (includes two torch.zeros fills)")
