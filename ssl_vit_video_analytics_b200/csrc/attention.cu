@@ -1,16 +1,19 @@
-// K2 — flash attention forward / backward on tcgen05 + TMEM (sm_100a), non-causal, no mask, no dropout.
-// Replaces F.scaled_dot_product_attention (tiny_vit.py:103) and the attention core of nn.TransformerEncoderLayer
-// (mae_vit_adapter.py:40-48). Input is the packed projection qkv[B, L, 3, H, hd]; q/k/v and the per-head slices are
-// addressed through TMA tensor-map coordinates, so no permute/contiguous copies are ever made.
+// K2 — flash attention forward / backward on tcgen05 + TMEM (sm_100a), non-causal, no mask, optional in-kernel dropout of
+// the attention probabilities. Replaces F.scaled_dot_product_attention (tiny_vit.py:103) and the attention core of
+// nn.TransformerEncoderLayer (mae_vit_adapter.py:40-48). Input is the packed projection qkv[B, L, 3, H, hd]; q/k/v and the
+// per-head slices are addressed through TMA tensor-map coordinates, so no permute/contiguous copies are ever made.
 //
-// All three kernels share one skeleton: a CTA owns 128 rows (TMEM lanes); "score-like" tiles are produced by UMMA into
-// TMEM, four warps (one thread per row) turn them into bf16 operand tiles written to shared memory in the canonical
-// K-major 128B-swizzle layout, and a second UMMA consumes those tiles. Two CTAs are co-resident per SM so one CTA's
-// exp/elementwise phase overlaps the other's tensor-core phase.
+// All kernels here share one skeleton: a CTA owns 128 rows (TMEM lanes) and has 256 threads = a control warpgroup (warp 0
+// issues the UMMAs, warp 1 the TMA loads; shrunk to 40 registers) and a row warpgroup (one thread per row, grown to 216
+// registers with setmaxnreg). "Score-like" tiles are produced by UMMA into TMEM; a row thread pulls its whole row into
+// registers with back-to-back tcgen05.ld (one wait) and hands the columns straight back, so the next tile is computed
+// underneath the element-wise phase. Two CTAs are co-resident per SM.
 //
-//   forward : S = Q K^T -> online softmax -> P (bf16, TMEM A-operand) -> O += P V_j accumulated in TMEM (lazy rescale)
-//   dQ      : S = Q K^T, dP = dO V^T -> dS = P*(dP - delta)*scale (smem) -> dQ += dS K          (TMEM accumulate)
-//   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem) -> dV += P^T dO, dK += dS^T Q      (TMEM accumulate)
+//   forward : S = Q K^T -> online softmax -> P (bf16, written back to TMEM as the A operand) -> O += P V_j in TMEM (lazy rescale)
+//   dQ      : S = Q K^T, dP = dO V^T -> dS = P*(dP - delta) (smem operand tile) -> dQ += dS K          (TMEM accumulate)
+//   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem operand tiles) -> dV += P^T dO, dK += dS^T Q
+// The dQ + dK/dV pair serves head_dim 32, short sequences and callers without an fp32 dQ workspace; head_dim 64 otherwise
+// runs the single-pass backward in attention_bwd_fused.cu.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/vmae.h"
