@@ -83,6 +83,17 @@ int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 /* The keep mask the two calls above use, materialised as uint8 [B, H, L, L] (1 = kept). Test/debug helper. */
 int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_drop, unsigned long long seed, void* stream);
 
+/* ---- stack-2 latent losses on gathered rows (mae/losses.py:19-63, called from tinyvit_mae.py / mae/engine.py) ----------
+ * pred, target: [rows, cols] bf16 or fp32. mode 0 = L2 (normalize != 0: target rows normalised with the biased variance,
+ * eps inside the sqrt — :36-38), 1 = L1, 2 = cosine (eps = F.normalize's). loss: device scalar; partials: fp32 workspace
+ * of vmae_row_loss_grid(rows) elements (per-block sums, added in a fixed order: deterministic). The target is detached in
+ * the reference, so backward produces dpred only (dtype of pred); gout: device scalar (upstream gradient of the loss). */
+int vmae_row_loss_grid(long long rows);
+int vmae_row_loss_fwd(const void* pred, int pred_dtype, const void* target, int target_dtype, long long rows, int cols, int mode,
+                      int normalize, float eps, float* partials, float* loss, void* stream);
+int vmae_row_loss_bwd(const void* pred, int pred_dtype, const void* target, int target_dtype, long long rows, int cols, int mode,
+                      int normalize, float eps, const float* gout, void* dpred, void* stream);
+
 /* ---- element dropout (nn.Dropout inside nn.TransformerEncoderLayer: dropout / dropout1 / dropout2, mae_vit_adapter.py:40-47)
  * dst[i] = (add ? add[i] : 0) + keep(seed, i) * src[i] / (1 - p).  src: bf16 or fp32 (src_dtype); add: optional fp32 (the
  * residual stream); dst: bf16 or fp32 (dst_dtype), may alias src. The same (p_drop, seed) reproduces the same mask, which is

@@ -360,6 +360,121 @@ __global__ void __launch_bounds__(MO_THREADS) pos_rows_bwd_kernel(const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stack-2 latent-space losses on gathered rows [rows, cols] (mae/losses.py:19-63): mode 0 = L2 (target optionally
+// normalised per row with the BIASED variance, eps inside the sqrt, :36-38), 1 = L1, 2 = cosine (F.normalize eps). One warp
+// per row; per-block partial sums are written out and added in a fixed order by the finalize kernel (deterministic).
+// The target is a detached tensor in the reference (tinyvit_mae.py:112), so only pred receives a gradient.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RL_THREADS = 256;
+template <typename T>
+__device__ __forceinline__ float rl_ld(const T* p, long long i);
+template <>
+__device__ __forceinline__ float rl_ld<float>(const float* p, long long i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float rl_ld<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float rl_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// per-row quantities shared by forward and backward
+template <typename PT, typename TT>
+__device__ __forceinline__ void rl_row_stats(const PT* pred, const TT* target, long long base, int cols, int lane, int mode, int normalize, float eps,
+                                             float& a, float& b, float& c) {
+  // mode 0: a = target mean, b = 1/sqrt(var + eps) (or 0, 1 without normalisation); mode 2: a = |p|^2, b = |t|^2, c = p.t
+  a = 0.f; b = 1.f; c = 0.f;
+  if (mode == 0 && normalize) {
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < cols; i += 32) { const float t = rl_ld<TT>(target, base + i); s += t; q = fmaf(t, t, q); }
+    s = rl_warp_sum(s); q = rl_warp_sum(q);
+    a = s / cols;
+    b = rsqrtf(fmaxf(q / cols - a * a, 0.f) + eps);
+  } else if (mode == 2) {
+    float pp = 0.f, tt = 0.f, pt = 0.f;
+    for (int i = lane; i < cols; i += 32) {
+      const float x = rl_ld<PT>(pred, base + i), t = rl_ld<TT>(target, base + i);
+      pp = fmaf(x, x, pp); tt = fmaf(t, t, tt); pt = fmaf(x, t, pt);
+    }
+    a = rl_warp_sum(pp); b = rl_warp_sum(tt); c = rl_warp_sum(pt);
+  }
+}
+template <typename PT, typename TT>
+__global__ void __launch_bounds__(RL_THREADS) row_loss_fwd_kernel(const PT* __restrict__ pred, const TT* __restrict__ target, long long rows, int cols,
+                                                                  int mode, int normalize, float eps, float* __restrict__ partials) {
+  __shared__ float red[RL_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (long long r = (long long)blockIdx.x * (RL_THREADS / 32) + warp; r < rows; r += (long long)gridDim.x * (RL_THREADS / 32)) {
+    const long long base = r * cols;
+    float a, b, c;
+    rl_row_stats<PT, TT>(pred, target, base, cols, lane, mode, normalize, eps, a, b, c);
+    if (mode == 2) {
+      if (lane == 0) acc += c / (fmaxf(sqrtf(a), eps) * fmaxf(sqrtf(b), eps));   // cosine of the row
+    } else {
+      float s = 0.f;
+      for (int i = lane; i < cols; i += 32) {
+        const float d = rl_ld<PT>(pred, base + i) - (rl_ld<TT>(target, base + i) - a) * b;
+        s += (mode == 0) ? d * d : fabsf(d);
+      }
+      acc += s;   // every lane keeps its share; reduced below
+    }
+  }
+  acc = rl_warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < RL_THREADS / 32; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+__global__ void row_loss_finalize_kernel(const float* __restrict__ partials, int n, long long rows, int cols, int mode, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < n; ++i) t += partials[i];
+    *loss = (mode == 2) ? 1.0f - t / (float)rows : t / ((float)rows * (float)cols);
+  }
+}
+template <typename PT, typename TT, typename GT>
+__global__ void __launch_bounds__(RL_THREADS) row_loss_bwd_kernel(const PT* __restrict__ pred, const TT* __restrict__ target, long long rows, int cols,
+                                                                  int mode, int normalize, float eps, const float* __restrict__ gout,
+                                                                  GT* __restrict__ dpred) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float g = __ldg(gout);
+  for (long long r = (long long)blockIdx.x * (RL_THREADS / 32) + warp; r < rows; r += (long long)gridDim.x * (RL_THREADS / 32)) {
+    const long long base = r * cols;
+    float a, b, c;
+    rl_row_stats<PT, TT>(pred, target, base, cols, lane, mode, normalize, eps, a, b, c);
+    if (mode == 2) {
+      const float np = fmaxf(sqrtf(a), eps), nt = fmaxf(sqrtf(b), eps);
+      const float cosv = c / (np * nt);
+      const bool clamped = sqrtf(a) <= eps;   // F.normalize divides by the constant eps there: d(p/eps) has no projection term
+      for (int i = lane; i < cols; i += 32) {
+        const float x = rl_ld<PT>(pred, base + i), t = rl_ld<TT>(target, base + i);
+        const float d = clamped ? (t / nt) / np : (t / nt - cosv * x / np) / np;
+        const float v = -g / (float)rows * d;
+        if (sizeof(GT) == 2) reinterpret_cast<__nv_bfloat16*>(dpred)[base + i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(dpred)[base + i] = v;
+      }
+    } else {
+      const float k = g / ((float)rows * (float)cols);
+      for (int i = lane; i < cols; i += 32) {
+        const float d = rl_ld<PT>(pred, base + i) - (rl_ld<TT>(target, base + i) - a) * b;
+        const float v = (mode == 0) ? 2.0f * k * d : k * ((d > 0.f) - (d < 0.f));
+        if (sizeof(GT) == 2) reinterpret_cast<__nv_bfloat16*>(dpred)[base + i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(dpred)[base + i] = v;
+      }
+    }
+  }
+}
+static inline int rl_grid(long long rows) {
+  long long g = (rows + RL_THREADS / 32 - 1) / (RL_THREADS / 32);
+  const long long cap = (long long)num_sms() * 4;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
 }  // namespace vmae
 
 using namespace vmae;
@@ -458,6 +573,45 @@ extern "C" int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtp
   VMAE_CHECK_ARG(dx && vis_idx && dtpos && dspos && B > 0 && Tp > 0 && n_vis > 0 && D % 4 == 0, "vmae_pos_rows_bwd: bad args");
   const long long rows = (long long)B * Tp * n_vis;
   pos_rows_bwd_kernel<<<mo_grid(rows), MO_THREADS, 0, (cudaStream_t)stream>>>(dx, vis_idx, dtpos, dspos, B, Tp, n_vis, D);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+extern "C" int vmae_row_loss_grid(long long rows) { return rl_grid(rows); }
+
+extern "C" int vmae_row_loss_fwd(const void* pred, int pred_dtype, const void* target, int target_dtype, long long rows, int cols, int mode,
+                                 int normalize, float eps, float* partials, float* loss, void* stream) {
+  VMAE_CHECK_ARG(pred && target && partials && loss, "vmae_row_loss_fwd: null pointer");
+  VMAE_CHECK_ARG(rows > 0 && cols > 0 && mode >= 0 && mode <= 2, "vmae_row_loss_fwd: bad rows=%lld cols=%d mode=%d", rows, cols, mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = rl_grid(rows);
+#define RL_FWD(PT, TT) row_loss_fwd_kernel<PT, TT><<<grid, RL_THREADS, 0, s>>>((const PT*)pred, (const TT*)target, rows, cols, mode, normalize, eps, partials)
+  if (pred_dtype == VMAE_DTYPE_BF16 && target_dtype == VMAE_DTYPE_BF16) RL_FWD(__nv_bfloat16, __nv_bfloat16);
+  else if (pred_dtype == VMAE_DTYPE_BF16 && target_dtype == VMAE_DTYPE_F32) RL_FWD(__nv_bfloat16, float);
+  else if (pred_dtype == VMAE_DTYPE_F32 && target_dtype == VMAE_DTYPE_BF16) RL_FWD(float, __nv_bfloat16);
+  else if (pred_dtype == VMAE_DTYPE_F32 && target_dtype == VMAE_DTYPE_F32) RL_FWD(float, float);
+  else return fail(VMAE_ERR_BAD_ARG, "vmae_row_loss_fwd: bad dtypes %d/%d", pred_dtype, target_dtype);
+#undef RL_FWD
+  VMAE_LAUNCH_CHECK();
+  row_loss_finalize_kernel<<<1, 32, 0, s>>>(partials, grid, rows, cols, mode, loss);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+extern "C" int vmae_row_loss_bwd(const void* pred, int pred_dtype, const void* target, int target_dtype, long long rows, int cols, int mode,
+                                 int normalize, float eps, const float* gout, void* dpred, void* stream) {
+  VMAE_CHECK_ARG(pred && target && gout && dpred, "vmae_row_loss_bwd: null pointer");
+  VMAE_CHECK_ARG(rows > 0 && cols > 0 && mode >= 0 && mode <= 2, "vmae_row_loss_bwd: bad rows=%lld cols=%d mode=%d", rows, cols, mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = rl_grid(rows);
+  // dpred has the dtype of pred
+#define RL_BWD(PT, TT) row_loss_bwd_kernel<PT, TT, PT><<<grid, RL_THREADS, 0, s>>>((const PT*)pred, (const TT*)target, rows, cols, mode, normalize, eps, gout, (PT*)dpred)
+  if (pred_dtype == VMAE_DTYPE_BF16 && target_dtype == VMAE_DTYPE_BF16) RL_BWD(__nv_bfloat16, __nv_bfloat16);
+  else if (pred_dtype == VMAE_DTYPE_BF16 && target_dtype == VMAE_DTYPE_F32) RL_BWD(__nv_bfloat16, float);
+  else if (pred_dtype == VMAE_DTYPE_F32 && target_dtype == VMAE_DTYPE_BF16) RL_BWD(float, __nv_bfloat16);
+  else if (pred_dtype == VMAE_DTYPE_F32 && target_dtype == VMAE_DTYPE_F32) RL_BWD(float, float);
+  else return fail(VMAE_ERR_BAD_ARG, "vmae_row_loss_bwd: bad dtypes %d/%d", pred_dtype, target_dtype);
+#undef RL_BWD
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }

@@ -1,7 +1,8 @@
 """Drop-in for `src/mae/losses.py` (:19-144): latent-space MAE losses on gathered rows [N_mask, D].
-Per-row normalisation uses the BIASED variance and eps=1e-6 inside the sqrt (:36-38). These operate on a few thousand
-rows and are expressed with tensor ops on whatever device the inputs live on; the pixel-space loss of the training
-step is the fused kernel `ops.masked_mse`."""
+Per-row normalisation uses the BIASED variance and eps=1e-6 inside the sqrt (:36-38). CUDA tensors go to the fused row-loss
+kernels (`vmae_row_loss_fwd/bwd`: one pass for statistics + loss, one for the gradient; the target is detached, as at the
+reference's call site tinyvit_mae.py:112). CPU tensors keep the reference's tensor-op formulation (the reference's losses are
+device-agnostic and its CPU tests call them); the pixel-space loss of the training step is `ops.masked_mse`."""
 from __future__ import annotations
 
 import torch
@@ -14,17 +15,33 @@ def _normalise_rows(t: torch.Tensor) -> torch.Tensor:
     return (t - mu) / (var + 1.0e-6).sqrt()
 
 
+def _on_gpu(pred, target) -> bool:
+    return pred.is_cuda and target.is_cuda and pred.dim() == 2 and pred.shape == target.shape and not target.requires_grad
+
+
 def mae_l2_loss(pred: torch.Tensor, target: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    if _on_gpu(pred, target):
+        from .. import ops
+
+        return ops.row_loss(pred, target, 0, normalize, 1.0e-6)
     if normalize:
         target = _normalise_rows(target)
     return ((pred - target) ** 2).mean()
 
 
 def mae_l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    if _on_gpu(pred, target):
+        from .. import ops
+
+        return ops.row_loss(pred, target, 1, False, 0.0)
     return (pred - target).abs().mean()
 
 
 def mae_cosine_loss(pred: torch.Tensor, target: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    if _on_gpu(pred, target):
+        from .. import ops
+
+        return ops.row_loss(pred, target, 2, False, eps)
     p = F.normalize(pred, dim=-1, eps=eps)
     t = F.normalize(target, dim=-1, eps=eps)
     return 1.0 - (p * t).sum(dim=-1).mean()

@@ -757,6 +757,48 @@ def masked_mse(pred, clip, mask, pt, ps, norm_pix=1):
     return MaskedMSEFn.apply(pred, clip, m8.contiguous(), pt, ps, norm_pix)
 
 
+class RowLossFn(torch.autograd.Function):
+    """Stack-2 latent losses on gathered rows (mae/losses.py:19-63): mode 0 = L2 (optionally with per-row biased-variance target
+    normalisation), 1 = L1, 2 = cosine. pred [rows, cols] bf16/fp32 gets the gradient; target is detached as in the reference."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mode, normalize, eps):
+        _need_cuda(pred, target)
+        assert pred.shape == target.shape and pred.dim() == 2
+        pred = pred.contiguous()
+        target = target.detach().contiguous()
+        if pred.dtype not in (BF16, F32):
+            pred = pred.float()
+        if target.dtype not in (BF16, F32):
+            target = target.float()
+        rows, cols = pred.shape
+        lib = L.load()
+        partials = torch.empty((lib.vmae_row_loss_grid(rows),), device=pred.device, dtype=F32)
+        loss = torch.empty((), device=pred.device, dtype=F32)
+        L.check(lib.vmae_row_loss_fwd(_p(pred), _dt(pred), _p(target), _dt(target), rows, cols, int(mode), int(bool(normalize)), float(eps),
+                                      _p(partials), _p(loss), _stream()), "vmae_row_loss_fwd")
+        _count(2)
+        ctx.save_for_backward(pred, target)
+        ctx.cfg = (int(mode), int(bool(normalize)), float(eps))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred, target = ctx.saved_tensors
+        mode, normalize, eps = ctx.cfg
+        rows, cols = pred.shape
+        dpred = torch.empty_like(pred)
+        g = gout.detach().float().contiguous()
+        L.check(L.load().vmae_row_loss_bwd(_p(pred), _dt(pred), _p(target), _dt(target), rows, cols, mode, normalize, eps, _p(g), _p(dpred),
+                                           _stream()), "vmae_row_loss_bwd")
+        _count()
+        return dpred, None, None, None, None
+
+
+def row_loss(pred, target, mode, normalize=True, eps=1e-6):
+    return RowLossFn.apply(pred, target, mode, normalize, eps)
+
+
 class GaussianNoiseFn(torch.autograd.Function):
     """z' = z + sigma * eps, eps ~ N(0, I) from Philox (privacy/feature_noise.py:4-7); gradient is the identity."""
 

@@ -448,3 +448,34 @@ def test_transformer_block_with_dropout_matches_explicit_masks(env):
             ref_g, our_g = prm.grad, got[f"{id(m)}.{kname}"]
             cos = float((ref_g.flatten().double() @ our_g.flatten().double()) / (ref_g.norm().double() * our_g.norm().double() + 1e-300))
             assert cos > 0.999, (type(m).__name__, kname, cos)
+
+
+@pytest.mark.parametrize("rows,cols,dt", [(1000, 576, torch.float32), (333, 192, torch.bfloat16), (7, 100, torch.float32)])
+def test_stack2_row_losses_fwd_bwd(env, rows, cols, dt):
+    """mae/losses.py:19-63 on CUDA tensors = the fused row-loss kernels; reference = the same formulas with tensor ops in fp32."""
+    from ssl_vit_video_analytics_b200.mae import losses as ML
+
+    ops, L, dev, g = env
+    pred = torch.randn(rows, cols, device=dev, generator=g).to(dt)
+    target = (torch.randn(rows, cols, device=dev, generator=g) * 2 + 0.5).to(dt)
+
+    def ref_l2(p, t, normalize):
+        if normalize:
+            t = (t - t.mean(-1, keepdim=True)) / (t.var(-1, keepdim=True, unbiased=False) + 1e-6).sqrt()
+        return ((p - t) ** 2).mean()
+
+    cases = [("l2n", lambda p, t: ML.mae_l2_loss(p, t, True), lambda p, t: ref_l2(p, t, True)),
+             ("l2", lambda p, t: ML.mae_l2_loss(p, t, False), lambda p, t: ref_l2(p, t, False)),
+             ("l1", ML.mae_l1_loss, lambda p, t: (p - t).abs().mean()),
+             ("cos", ML.mae_cosine_loss, lambda p, t: 1.0 - (F.normalize(p, dim=-1, eps=1e-6) * F.normalize(t, dim=-1, eps=1e-6)).sum(-1).mean())]
+    tol = 1e-5 if dt == torch.float32 else 2e-2
+    for name, ours, ref in cases:
+        po = pred.clone().requires_grad_(True)
+        lo = ours(po, target)
+        (lo * 1.7).backward()
+        pr = pred.float().clone().requires_grad_(True)
+        lr = ref(pr, target.float())
+        (lr * 1.7).backward()
+        assert abs(float(lo) - float(lr)) <= 1e-5 + 1e-4 * abs(float(lr)), (name, float(lo), float(lr))
+        assert relerr(po.grad, pr.grad) < tol, name
+    assert ML.mae_recon_loss(pred, target, "l1", False).is_cuda
