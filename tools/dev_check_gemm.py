@@ -135,7 +135,7 @@ def mode_perf():
         rows.append(("dgrad", _time(lambda: gemm(dy, N, 0, w, K, 1, M, K, N, out=dx))))
         dw = torch.zeros(N, K, device=dev, dtype=torch.float32)
         rows.append(("wgrad auto", _time(lambda: ops.linear_wgrad(dy, x))))
-        for ks in (4, 12, 24):
+        for ks in ((4, 8, 12, 16, 24, 32, 48) if len(sys.argv) > 3 else (4, 12, 24)):
             rows.append((f"wgrad ks={ks}", _time(lambda: gemm(dy, N, 1, x, K, 1, N, K, M, out=dw, out_fp32=True, accumulate=True, k_splits=ks))))
         print(f"perf {tag} M={M} N={N} K={K}: " + " | ".join(f"{n} {ms*1e3:.0f}us {fl/ms/1e9:.0f}TF" for n, ms in rows), flush=True)
     return True
