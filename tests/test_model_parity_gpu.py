@@ -231,3 +231,52 @@ def test_decoder_dropout_default_config_trains_and_is_reproducible():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         e1, e2 = model(clip, mask).float(), model(clip, mask).float()
     assert torch.equal(e1, e2)                                       # eval: no dropout
+
+
+def test_finetune_classifier_vs_oracle():
+    """frames -> TinyViT.forward (4 stages) -> GAP + temporal mean -> Linear -> CE against the fp32 oracle restatement of
+    the same encoder, same weights (train-mode BatchNorm, drop-path off)."""
+    import torch.nn.functional as F
+
+    from ssl_vit_video_analytics_b200.models import TinyViTVideoClassifier, apply_finetune_mode, tiny_vit_21m_variant
+
+    torch.manual_seed(0)
+    enc = tiny_vit_21m_variant(img_size=64, use_checkpoint=False, drop_path_rate=0.0)
+    model = TinyViTVideoClassifier(num_classes=11, encoder=enc)
+    sd = R.perturb_state_dict(model.state_dict(), seed=5)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    clip = torch.randn(2, 3, 3, 64, 64, generator=g)
+    labels = torch.tensor([3, 7])
+    # oracle
+    sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and "running" not in k else v) for k, v in sd.items()}
+    frames = clip.permute(0, 2, 1, 3, 4).flatten(0, 1)
+    feat = R.tinyvit_forward(sdg, frames, prefix="backbone.", num_stages=4)
+    z = feat.mean(dim=(2, 3)).view(2, 3, -1).mean(dim=1)
+    logits_o = F.linear(z, sdg["classifier.weight"], sdg["classifier.bias"])
+    loss_o = F.cross_entropy(logits_o, labels)
+    loss_o.backward()
+    ref = {k: v.grad for k, v in sdg.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    # ours
+    model = model.cuda().train()
+    assert apply_finetune_mode(model, "ft_ssl") is True
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = model(clip.cuda())
+    loss = F.cross_entropy(logits.float(), labels.cuda())
+    loss.backward()
+    assert abs(float(loss) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o)) + 1e-3
+    assert cosine(logits.detach().float().cpu(), logits_o.detach()) > 0.999
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    big = [k for k in ref if k in ours and float(ref[k].norm()) > 1e-6]
+    glob = cosine(torch.cat([ours[k].flatten() for k in big]), torch.cat([ref[k].flatten() for k in big]))
+    assert glob > 0.995, glob
+    # linear probe: the backbone is frozen, only the head trains
+    assert apply_finetune_mode(model, "linear_probe") is False and not any(p.requires_grad for p in model.backbone.parameters())
+    assert apply_finetune_mode(model, "two_stage", epoch=0, stage1_epochs=2) is False
+    assert apply_finetune_mode(model, "two_stage", epoch=2, stage1_epochs=2) is True
+    # privacy-style feature noise on the pooled embedding: same mean, variance sigma^2
+    model.eval()
+    model.noise_sigma = 0.0
+    with torch.no_grad():
+        z0 = model.video_embedding(clip.cuda())
+    assert z0.shape == (2, 576) and z0.dtype == torch.float32
