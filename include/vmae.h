@@ -83,6 +83,13 @@ int vmae_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 /* The keep mask the two calls above use, materialised as uint8 [B, H, L, L] (1 = kept). Test/debug helper. */
 int vmae_attn_dropout_mask(void* mask, int B, int L, int H, float p_drop, unsigned long long seed, void* stream);
 
+/* ---- input pipeline tail (datasets/mae_loader.py:63-77) ------------------------------------------------------
+ * frames_u8: device uint8 [B, T, H, W, 3] (decoded RGB frames); clip: device fp32 [B, 3, T, H, W] =
+ * ((u / 255) - mean[c]) / std[c] per channel (ToTensor + Normalize), channels reversed when flip_channels != 0 (the loader's
+ * `img[[2, 1, 0]]`), time moved behind the channel axis. mean3 / std3 are HOST arrays of 3 floats. */
+int vmae_frames_to_clip(const void* frames_u8, float* clip, int B, int T, int H, int W, const float* mean3, const float* std3,
+                        int flip_channels, void* stream);
+
 /* ---- stack-2 latent losses on gathered rows (mae/losses.py:19-63, called from tinyvit_mae.py / mae/engine.py) ----------
  * pred, target: [rows, cols] bf16 or fp32. mode 0 = L2 (normalize != 0: target rows normalised with the biased variance,
  * eps inside the sqrt — :36-38), 1 = L1, 2 = cosine (eps = F.normalize's). loss: device scalar; partials: fp32 workspace

@@ -27,6 +27,7 @@ SIGNATURES = {
     "vmae_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
     "vmae_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
     "vmae_attn_dropout_mask": [_p, _i, _i, _i, _f, _ull, _p],
+    "vmae_frames_to_clip": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p],
     "vmae_row_loss_grid": [_ll],
     "vmae_row_loss_fwd": [_p, _i, _p, _i, _ll, _i, _i, _i, _f, _p, _p, _p],
     "vmae_row_loss_bwd": [_p, _i, _p, _i, _ll, _i, _i, _i, _f, _p, _p, _p],

@@ -475,6 +475,26 @@ static inline int rl_grid(long long rows) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Input pipeline tail: decoded uint8 frames [B, T, H, W, 3] -> normalised fp32 clip [B, 3, T, H, W], i.e. what
+// transforms.ToTensor + Normalize(mean, std) produce per frame followed by the loader's channel reversal and the
+// [T, C, H, W] -> [C, T, H, W] permute (mae_loader.py:63-77). One thread per pixel: three byte loads, three coalesced stores.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frames_to_clip_kernel(const uint8_t* __restrict__ frames, float* __restrict__ clip, long long npix, long long thw,
+                                                             float s0, float s1, float s2, float b0, float b1, float b2, int flip) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < npix; i += gridDim.x * 256LL) {
+    const uint8_t* px = frames + 3 * i;
+    const float v0 = fmaf(static_cast<float>(px[0]), s0, b0), v1 = fmaf(static_cast<float>(px[1]), s1, b1),
+                v2 = fmaf(static_cast<float>(px[2]), s2, b2);
+    const long long bidx = i / thw, r = i % thw;
+    float* o = clip + bidx * 3 * thw + r;
+    o[0] = flip ? v2 : v0;
+    o[thw] = v1;
+    o[2 * thw] = flip ? v0 : v2;
+  }
+}
+
 }  // namespace vmae
 
 using namespace vmae;
@@ -612,6 +632,24 @@ extern "C" int vmae_row_loss_bwd(const void* pred, int pred_dtype, const void* t
   else if (pred_dtype == VMAE_DTYPE_F32 && target_dtype == VMAE_DTYPE_F32) RL_BWD(float, float);
   else return fail(VMAE_ERR_BAD_ARG, "vmae_row_loss_bwd: bad dtypes %d/%d", pred_dtype, target_dtype);
 #undef RL_BWD
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+
+extern "C" int vmae_frames_to_clip(const void* frames_u8, float* clip, int B, int T, int H, int W, const float* mean3, const float* std3,
+                                   int flip_channels, void* stream) {
+  VMAE_CHECK_ARG(frames_u8 && clip && mean3 && std3 && B > 0 && T > 0 && H > 0 && W > 0, "vmae_frames_to_clip: bad args");
+  const long long thw = (long long)T * H * W, npix = (long long)B * thw;
+  float s[3], b[3];
+  for (int c = 0; c < 3; ++c) {   // (u/255 - mean) / std = u * (1/(255 std)) - mean/std; mean3/std3 are HOST pointers
+    VMAE_CHECK_ARG(std3[c] != 0.f, "vmae_frames_to_clip: std[%d] == 0", c);
+    s[c] = 1.0f / (255.0f * std3[c]);
+    b[c] = -mean3[c] / std3[c];
+  }
+  long long g = (npix + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  frames_to_clip_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames_u8, clip, npix, thw, s[0], s[1], s[2], b[0], b[1], b[2],
+                                                                     flip_channels);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }

@@ -757,6 +757,24 @@ def masked_mse(pred, clip, mask, pt, ps, norm_pix=1):
     return MaskedMSEFn.apply(pred, clip, m8.contiguous(), pt, ps, norm_pix)
 
 
+def frames_to_clip(frames_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), flip_channels=True, out=None):
+    """Decoded uint8 frames [B, T, H, W, 3] on the GPU -> normalised fp32 clip [B, 3, T, H, W] (ToTensor + Normalize + the loader's
+    channel reversal and permute, mae_loader.py:63-77): the host uploads a quarter of the bytes of a float clip."""
+    import ctypes
+
+    _need_cuda(frames_u8)
+    assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 5 and frames_u8.shape[-1] == 3 and frames_u8.is_contiguous()
+    B, T, H, W, _ = frames_u8.shape
+    if out is None:
+        out = torch.empty((B, 3, T, H, W), device=frames_u8.device, dtype=F32)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    L.check(L.load().vmae_frames_to_clip(_p(frames_u8), _p(out), B, T, H, W, ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p),
+                                         1 if flip_channels else 0, _stream()), "vmae_frames_to_clip")
+    _count()
+    return out
+
+
 class RowLossFn(torch.autograd.Function):
     """Stack-2 latent losses on gathered rows (mae/losses.py:19-63): mode 0 = L2 (optionally with per-row biased-variance target
     normalisation), 1 = L1, 2 = cosine. pred [rows, cols] bf16/fp32 gets the gradient; target is detached as in the reference."""

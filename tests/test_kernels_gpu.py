@@ -479,3 +479,20 @@ def test_stack2_row_losses_fwd_bwd(env, rows, cols, dt):
         assert abs(float(lo) - float(lr)) <= 1e-5 + 1e-4 * abs(float(lr)), (name, float(lo), float(lr))
         assert relerr(po.grad, pr.grad) < tol, name
     assert ML.mae_recon_loss(pred, target, "l1", False).is_cuda
+
+
+@pytest.mark.parametrize("flip", [True, False])
+def test_frames_to_clip_matches_loader_transform(env, flip):
+    """uint8 frames -> ToTensor + Normalize + channel reversal + [T,C,H,W]->[C,T,H,W] (mae_loader.py:63-77), done on the GPU."""
+    ops, L, dev, g = env
+    B, T, H, W = 2, 3, 17, 21
+    frames = torch.randint(0, 256, (B, T, H, W, 3), device=dev, dtype=torch.uint8, generator=g)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = frames.float().permute(0, 1, 4, 2, 3) / 255.0                                  # [B, T, C, H, W] = ToTensor per frame
+    x = (x - torch.tensor(mean, device=dev).view(1, 1, 3, 1, 1)) / torch.tensor(std, device=dev).view(1, 1, 3, 1, 1)
+    if flip:
+        x = x[:, :, [2, 1, 0]]
+    ref = x.permute(0, 2, 1, 3, 4).contiguous()
+    got = ops.frames_to_clip(frames, mean, std, flip_channels=flip)
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert float((got - ref).abs().max()) < 2e-6
