@@ -1,4 +1,5 @@
 // libvmae_sm100a.so — library-wide host plumbing (see include/vmae.h for the C ABI).
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/vmae.h"
 
@@ -69,6 +70,14 @@ int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uin
     return fail(VMAE_ERR_DRIVER, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
   return VMAE_OK;
+}
+
+bool pdl_enabled(int group) {
+  static const int mask = []() {
+    const char* e = getenv("VMAE_PDL");
+    return e ? atoi(e) : PDL_DEFAULT_MASK;
+  }();
+  return (mask & group) != 0;
 }
 
 }  // namespace vmae

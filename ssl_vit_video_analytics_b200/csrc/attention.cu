@@ -156,6 +156,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tS = tmem, tO = tmem + BKV, tP = tmem + BKV + HD;   // P: bf16 A-operand, BKV/2 packed columns
+  pdl_wait();               // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp < 4) {
     setmaxnreg_dec<ATT_CTRL_REGS>();
@@ -364,6 +366,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                          float* __restrict__ delta, int B, int L, int H) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = static_cast<long long>(B) * L * H;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -467,6 +471,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_res_qkv, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tT0 = tmem, tT1 = tmem + BS, tA0 = tmem + 2 * BS, tA1 = tmem + 2 * BS + HD;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < 4) {
     setmaxnreg_dec<ATT_CTRL_REGS>();
@@ -709,11 +715,11 @@ static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   if (drop.thr > 0) {
     auto kern = attn_fwd_kernel<HD, BKV, true>;
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
   } else {
     auto kern = attn_fwd_kernel<HD, BKV, false>;
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
   }
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
@@ -737,13 +743,13 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
   if (drop.thr > 0) {
     auto kern = attn_bwd_kernel<HD, BS, MODE, true>;
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H,
-                                                             scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta,
+                         (__nv_bfloat16*)dqkv, L, H, scale, drop));
   } else {
     auto kern = attn_bwd_kernel<HD, BS, MODE, false>;
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    kern<<<grid, ATT_FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta, (__nv_bfloat16*)dqkv, L, H,
-                                                             scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, m_res_qkv, m_str_qkv, m_res_do, m_str_do, lse, delta,
+                         (__nv_bfloat16*)dqkv, L, H, scale, drop));
   }
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
@@ -810,8 +816,7 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
   if (grid > num_sms() * 16) grid = num_sms() * 16;
   int rc;
   if (hd == 64) {
-    attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
-    VMAE_LAUNCH_CHECK();
+    VMAE_CUDA(launch_pdl(PDL_ATTN, attn_delta_kernel<64>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H));
     // single-pass kernel (5 GEMM units, one exponential per score, dQ reduced through L2) when the caller provides the fp32
     // dQ accumulator; the two-kernel form otherwise
     if (dq_accum != nullptr) return attn_bwd_fused_hd64(qkv, dout, lse, delta, dqkv, dq_accum, B, L, H, scale, p_drop, seed, s);
@@ -820,8 +825,7 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
     return launch_bwd<64, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
   }
   if (hd == 32) {
-    attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H);
-    VMAE_LAUNCH_CHECK();
+    VMAE_CUDA(launch_pdl(PDL_ATTN, attn_delta_kernel<32>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H));
     rc = launch_bwd<32, 64, BWD_DQ>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);
     if (rc) return rc;
     return launch_bwd<32, 64, BWD_DKDV>(qkv, dout, lse, delta, dqkv, B, L, H, scale, p_drop, seed, s);

@@ -155,6 +155,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
+  pdl_wait();               // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp < 4) {
     setmaxnreg_dec<C::CTRL_REGS>();
@@ -467,6 +469,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 // dq (bf16, q slot of dqkv[B, L, 3, H, 64]) = scale * dq_accum (fp32 [B, L, H*64])
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H,
                                                               float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int vec_per_row = H * fb::HD / 4;
   const long long total = rows * vec_per_row;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += gridDim.x * 256LL) {
@@ -518,17 +522,16 @@ int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, con
   const AttnDrop drop = make_attn_drop(p_drop, seed);
   if (drop.thr > 0) {
     VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attn_bwd_fused_kernel<G, true><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN_FUSED, attn_bwd_fused_kernel<G, true>, dim3(grid), dim3(Cfg<G>::THREADS), SMEM_BYTES, stream, m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop));
   } else {
     VMAE_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attn_bwd_fused_kernel<G, false><<<grid, Cfg<G>::THREADS, SMEM_BYTES, stream>>>(m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop);
+    VMAE_CUDA(launch_pdl(PDL_ATTN_FUSED, attn_bwd_fused_kernel<G, false>, dim3(grid), dim3(Cfg<G>::THREADS), SMEM_BYTES, stream, m_qkv, m_do, m_dq, lse, delta, (__nv_bfloat16*)dqkv, L, H, B, scale, drop));
   }
   VMAE_LAUNCH_CHECK();
   const long long rows = (long long)B * L;
   long long g = (rows * (H * HD / 4) + 255) / 256;
   if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
-  attn_dq_convert_kernel<<<(unsigned)g, 256, 0, stream>>>(dq_accum, (__nv_bfloat16*)dqkv, rows, H, scale);
-  VMAE_LAUNCH_CHECK();
+  VMAE_CUDA(launch_pdl(PDL_ATTN_FUSED, attn_dq_convert_kernel, dim3((unsigned)g), dim3(256), 0, stream, (const float*)dq_accum, (__nv_bfloat16*)dqkv, rows, H, scale));
   return VMAE_OK;
 }
 

@@ -1,6 +1,7 @@
 // K3 / K8 / K9 and small HBM-bound helpers: LayerNorm fwd/bwd, dtype casts, bias-gradient column sums,
 // Gaussian feature noise (Philox), fp32 scale/axpy. One warp owns one row; 128-bit loads; warp-shuffle reductions.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/vmae.h"
 
 namespace vmae {
@@ -63,6 +64,8 @@ __global__ void __launch_bounds__(EW_THREADS) layernorm_fwd_kernel(const XT* __r
                                                                    const float* __restrict__ beta, YT* __restrict__ y,
                                                                    float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                    long long rows, int cols, float eps) {
+  pdl_wait();   // programmatic dependent launch: this grid may have started while its producer was still draining
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
   const long long warp_stride = (long long)gridDim.x * EW_WARPS;
@@ -147,6 +150,8 @@ __global__ void __launch_bounds__(EW_THREADS, (NV <= 4) ? 2 : 1) layernorm_bwd_k
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                    long long rows, int cols) {
   extern __shared__ float red_smem[];  // [EW_WARPS][2][cols]
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * EW_WARPS + warp;
@@ -450,7 +455,7 @@ static int ln_fwd_dispatch(const void* x, const float* gamma, const float* beta,
   const int grid = ew_grid(rows, EW_WARPS);
 #define LN_CASE(NV)                                                                                                             \
   case NV:                                                                                                                      \
-    layernorm_fwd_kernel<XT, YT, NV><<<grid, EW_THREADS, 0, s>>>((const XT*)x, gamma, beta, (YT*)y, mean, rstd, rows, cols, eps); \
+    VMAE_CUDA(launch_pdl(PDL_LN, layernorm_fwd_kernel<XT, YT, NV>, dim3(grid), dim3(EW_THREADS), 0, s, (const XT*)x, gamma, beta, (YT*)y, mean, rstd, rows, cols, eps)); \
     break;
   switch (nv) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -488,8 +493,8 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
   case NV: {                                                                                                             \
     auto k = layernorm_bwd_kernel<DT, XT, NV>;                                                                           \
     if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    k<<<grid, EW_THREADS, smem, s>>>((const DT*)dy, (const XT*)x, gamma, mean, rstd, dx_resid, dx_out,                   \
-                                     (__nv_bfloat16*)dx_out_bf16, dgamma, dbeta, rows, cols);                            \
+    VMAE_CUDA(launch_pdl(PDL_LN, k, dim3(grid), dim3(EW_THREADS), smem, s, (const DT*)dy, (const XT*)x, gamma, mean, rstd, dx_resid, dx_out,  \
+                         (__nv_bfloat16*)dx_out_bf16, dgamma, dbeta, rows, cols));                                        \
   } break;
   switch (nv) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

@@ -193,6 +193,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel; from here on this grid reads
+  // and writes global memory, so it waits for that kernel to complete, and lets the next kernel's CTAs start their prologue
+  // as soon as CTAs of this grid retire
+  pdl_wait();
+  pdl_launch_dependents();
 
   auto decode = [&](int unit, int& m0, int& n0, int& kb0, int& kb1) {
     const int nt = unit % n_tiles;
@@ -462,8 +467,7 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int grid, cudaStr
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(m.a, m.b, m.out, m.aux, p);
-  VMAE_LAUNCH_CHECK();
+  VMAE_CUDA(launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, m.a, m.b, m.out, m.aux, p));
   return VMAE_OK;
 }
 

@@ -100,6 +100,13 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (its CTAs
+// run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel in the stream is still
+// draining. pdl_wait() blocks until that previous grid has completed and its memory is visible — it must precede the first
+// global-memory access; pdl_launch_dependents() lets the next kernel's CTAs be scheduled as this grid's CTAs retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Register re-balancing between warpgroups (4 aligned warps): control warps give registers back to the CTA pool, the
 // row warps take them. All warps of the warpgroup must execute the same instruction; N is a multiple of 8.
 template <int N>
