@@ -496,3 +496,22 @@ def test_frames_to_clip_matches_loader_transform(env, flip):
     got = ops.frames_to_clip(frames, mean, std, flip_channels=flip)
     assert got.shape == ref.shape and got.dtype == torch.float32
     assert float((got - ref).abs().max()) < 2e-6
+
+
+def test_attn_bwd_c_abi_accepts_workspace_for_any_head_dim(env):
+    """vmae_attn_bwd with a dQ accumulator: head_dim 64 takes the single-pass kernel, head_dim 32 silently uses the two-kernel form
+    (the workspace is simply not needed) — same results either way."""
+    ops, L, dev, g = env
+    lib = L.load()
+    p = lambda t: t.data_ptr() if t is not None else None
+    st = torch.cuda.current_stream().cuda_stream
+    for (B, Lq, H, hd) in [(2, 256, 3, 32), (2, 256, 3, 64)]:
+        qkv = torch.randn(B, Lq, 3 * H * hd, device=dev, generator=g).bfloat16()
+        dout = torch.randn(B * Lq, H * hd, device=dev, generator=g).bfloat16()
+        out, lse = ops.attn_fwd(qkv, B, Lq, H, hd)
+        ref = ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, fused=False)
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(B, H, Lq, device=dev)
+        acc = torch.empty(B * Lq, H * hd, device=dev)
+        L.check(lib.vmae_attn_bwd(p(qkv), p(out), p(dout), p(lse), p(delta), p(acc), p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), 0.0, 0, st), "bwd")
+        assert relerr(dqkv, ref) < 1e-2
