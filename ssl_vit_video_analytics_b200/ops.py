@@ -110,10 +110,24 @@ def gemm(a, b, M, N, K, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, resi
     return out
 
 
-def _wgrad_splits(tokens: int, n_out: int, k_out: int) -> int:
-    tiles = ((n_out + 127) // 128) * ((k_out + 191) // 192)
+def _wgrad_splits(tokens: int, n_out: int, k_out: int, sms: int = 148) -> int:
+    """Split-K factor of dW[n_out, k_out] += dy^T x over `tokens`. Mirrors the kernel's tile choice (pick_block_n in gemm.cu: BLOCK_N
+    in {192, 128}, cost rounds * (BLOCK_N + 48)) and minimises rounds * (k-blocks per split * (BLOCK_N + 48) + epilogue): the number of
+    units should land just under a multiple of the SM count with the larger tile (measured on the decoder shapes: qkv 138 -> 100 us)."""
+    m_tiles = (n_out + 127) // 128
     kb = (tokens + 63) // 64
-    return max(1, min(kb, (2 * 148 + tiles - 1) // tiles))
+    best, best_cost = 1, None
+    for ks in range(1, min(kb, 64) + 1):
+        cand = []
+        for bn in (192, 128):
+            units = m_tiles * ((k_out + bn - 1) // bn) * ks
+            cand.append((((units + sms - 1) // sms) * (bn + 48), bn, units))
+        _, bn, units = min(cand)           # what the kernel will pick for this ks
+        rounds = (units + sms - 1) // sms
+        cost = rounds * (((kb + ks - 1) // ks) * (bn + 48) + 2500)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = ks, cost
+    return best
 
 
 def linear_fwd(x, w_bf16, bias=None, *, act=L.ACT_NONE, residual=None, aux_out=None, out_dtype=BF16):
