@@ -14,6 +14,7 @@
 //   dK/dV   : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem operand tiles) -> dV += P^T dO, dK += dS^T Q
 // The dQ + dK/dV pair serves head_dim 32, short sequences and callers without an fp32 dQ workspace; head_dim 64 otherwise
 // runs the single-pass backward in attention_bwd_fused.cu.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/vmae.h"

@@ -3,16 +3,18 @@
 // The two-kernel backward in attention.cu recomputes S and dP twice (7 GEMM units and 2 exponentials per score). This kernel
 // does the textbook 5 units and 1 exponential: a CTA owns 128 key/value rows (dK, dV accumulate in TMEM over the whole
 // query sweep) and, per 128-query block, also produces that block's partial dQ = dS K, which is added to an fp32
-// accumulator in global memory with TMA reduce-add (L2 atomics, 32 KB per block). One CTA per SM (it needs 512 TMEM
-// columns); 384 threads = a control warpgroup (TMA producer warp, UMMA issuer warp; shrunk to 40 registers) and eight row warps (a thread owns one key row / TMEM lane and
-// half of the query columns, so every SM sub-partition has two row warps whose phases overlap).
+// accumulator in global memory with TMA reduce-add (L2 atomics, one 32 x 32 box per row warp). Persistent, one CTA per SM
+// (it needs 448 TMEM columns); 384 threads = a control warpgroup (TMA producer warp, UMMA issuer warp; shrunk to 64 registers)
+// and eight row warps (216 registers): a row thread owns one QUERY row of the block (its lse and delta are two scalars in
+// registers) and half of the 128 key columns, so every SM sub-partition has two row warps whose phases overlap.
 //
-//   per query block i:   T0 = K Q_i^T   (S^T, 128 x 128)          T1 = V dO_i^T   (dP^T)
-//                        P^T = exp2(T0 * scale*log2e - lse_i),     dS^T = P^T * (T1 - delta_i)
-//                        dV += P^T dO_i   (A operand = P^T in TMEM)      dK += dS^T Q_i   (A = dS^T tile in smem, K-major)
-//                        dQ_i = dS K      (A = the same smem tile read MN-major: no transpose pass)
-// The per-column statistics (lse_i, delta_i) are staged in warp-private double-buffered shared arrays; the row warps never meet
-// at a CTA-wide barrier: they synchronise only through the mbarriers they share with the UMMA warp.
+//   per query block i:   T0 = Q_i K^T   (S, 128 q x 128 kv)         T1 = dO_i V^T   (dP)
+//                        P = exp2(T0 * scale*log2e - lse_q),         dS = P * (T1 - delta_q)      -> two [q x kv] bf16 tiles in smem
+//                        dV += P^T dO_i     dK += dS^T Q_i           (A operand = the P / dS tile read MN-major: no transpose pass)
+//                        dQ_i = dS K                                 (A operand = the dS tile read K-major)
+// The row warps never meet at a CTA-wide barrier: they synchronise only through the mbarriers they share with the UMMA warp.
+// (A first version kept key rows per thread and P^T in TMEM; it needed per-column statistics staged through shared memory —
+// 32 LDS.128 per thread and iteration and visible short-scoreboard stalls — and measured 1.3 % slower.)
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/vmae.h"
@@ -43,13 +45,13 @@ constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + TILE;
 constexpr int OFF_Y = OFF_V + TILE;        // [NS][2] tiles: Q_i, dO_i
 constexpr int OFF_E = OFF_Y + NS * 2 * TILE;       // dS^T: [128 key rows x 128 queries] bf16 = two 64-column SW128 chunks (32 KB)
-constexpr int OFF_DQ = OFF_E + 2 * TILE;           // dQ staging: two [128 x 32] fp32 SW128 boxes (32 KB)
-constexpr int OFF_STAT = OFF_DQ + 2 * TILE;        // per row warp: [2 buffers][lse*log2e (COLS) | delta (COLS)] fp32; 8 KB in total
-constexpr int OFF_BAR = OFF_STAT + 8 * 2 * 128 * 4;
+constexpr int OFF_P = OFF_E + 2 * TILE;            // P: same layout as the dS tile (32 KB)
+constexpr int OFF_DQ = OFF_P + 2 * TILE;           // dQ staging: two [128 x 32] fp32 SW128 boxes (32 KB)
+constexpr int OFF_BAR = OFF_DQ + 2 * TILE;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
 // TMEM columns
-constexpr uint32_t T0 = 0, T1 = 128, DK = 256, DV = 320, DQ = 384, TP = 448;
+constexpr uint32_t T0 = 0, T1 = 128, DK = 256, DV = 320, DQ = 384;
 constexpr float LOG2E_F = 1.4426950408889634f;
 }  // namespace fb
 
@@ -95,7 +97,7 @@ __device__ __forceinline__ void fb_tma_reduce_add_3d(const CUtensorMap* m, uint3
 }
 
 // map_qkv: 128-row boxes over qkv (K/V resident per work item, Q streamed); map_do: 128-row boxes over dO;
-// map_dq: fp32 [B, L, H*64], box 32 x 128.
+// map_dq: fp32 [B, L, H*64], box DQC x 32.
 // Persistent: grid = #SMs; a CTA walks work items w = (b, h, key tile) with stride gridDim.x (consecutive items share (b, h),
 // so co-running CTAs stream the same Q_i / dO_i blocks out of L2). TMEM is allocated once, the mbarrier phases run on across
 // items, and the next item's K/V load overlaps the current item's dK/dV read-out.
@@ -110,9 +112,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if (threadIdx.x == 0 && (sbase & 1023u) != 0) { printf("vmae attention: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
-  const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V, sE = sbase + OFF_E, sDQ = sbase + OFF_DQ;
+  const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V, sE = sbase + OFF_E, sP = sbase + OFF_P, sDQ = sbase + OFF_DQ;
   auto sY = [&](int s, int t) { return sbase + OFF_Y + (s * 2 + t) * TILE; };
-  float* stat = reinterpret_cast<float*>(smem_raw + OFF_STAT);
   const uint32_t bar = sbase + OFF_BAR;
   const uint32_t res_full = bar, t_full = bar + 8, t_free = bar + 16, p_ready = bar + 24, acc_done = bar + 32, kv_free = bar + 104;
   auto st_full = [&](int s) { return bar + 40 + 8 * s; };
@@ -182,8 +183,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   } else if (warp == 1) {
     if (elect_one()) {   // UMMA issuer
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, BQ, 0, 0);    // T = A(K-major) x B(K-major), N = 128
-      constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 0, 1);    // acc += A(K-major | TMEM) x B(MN-major), N = 64
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 1, 1);    // dQ = A(MN-major) x B(MN-major)
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);    // dQ = dS (K-major A) x K (MN-major B), N = 64
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, HD, 1, 1);    // dV / dK += P^T | dS^T (MN-major A) x dO | Q (MN-major B)
       // every operand tile sits at a fixed offset from the 1024-aligned smem base, so one descriptor (two registers) serves all
       // of them: only the 14-bit start-address field (bytes >> 4) differs
       const uint64_t d0 = umma_smem_desc(sbase, 0, 1024, 128);
@@ -191,16 +192,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       const uint64_t dV_k = d0 + (OFF_V >> 4);
       auto dQ_ = [&](int s) { return d0 + ((OFF_Y + (s * 2) * TILE) >> 4); };
       auto dO_ = [&](int s) { return d0 + ((OFF_Y + (s * 2 + 1) * TILE) >> 4); };
-      const uint64_t dE_k = d0 + (OFF_E >> 4);                                                   // dS^T, K-major: 64-query chunks 16 KB apart
-      const uint64_t dE_mn = umma_smem_desc(sbase, 128 * 128, 1024, 128) + (OFF_E >> 4);         // dS, MN-major: LBO = stride between the two 64-wide M chunks
+      const uint64_t dE_k = d0 + (OFF_E >> 4);                                                   // dS [q x kv], K-major: 64-key chunks 16 KB apart
+      const uint64_t dmn = umma_smem_desc(sbase, 128 * 128, 1024, 128);                          // MN-major: LBO = stride between the two 64-wide M chunks
+      const uint64_t dE_mn = dmn + (OFF_E >> 4), dP_mn = dmn + (OFF_P >> 4);                     // dS^T and P^T read out of the [q x kv] tiles
       auto issue_t = [&](uint32_t g) {
         const int s = g % NS;
         mbar_wait(st_full(s), (g / NS) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T0, dK_k + 2 * k, dQ_(s) + 2 * k, idesc_t, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T0, dQ_(s) + 2 * k, dK_k + 2 * k, idesc_t, k > 0);   // S = Q_i K^T
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T1, dV_k + 2 * k, dO_(s) + 2 * k, idesc_t, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem + T1, dO_(s) + 2 * k, dV_k + 2 * k, idesc_t, k > 0);   // dP = dO_i V^T
         umma_commit(t_full);
       };
       uint32_t gi = 0, item_n = 0;
@@ -224,14 +226,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
           tc_fence_after();
           ATT_STAMP(1, it, 3);
 #pragma unroll
-          for (int kk = 0; kk < BQ / 16; ++kk)   // dV += P^T dO_i  (contraction over the 128 queries)
-            umma_bf16_ts(tmem + DV, tmem + TP + kk * 8, dO_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
+          for (int kk = 0; kk < BQ / 16; ++kk)   // dV += P^T dO_i  (contraction over the 128 queries; P^T = the P tile read MN-major)
+            umma_bf16(tmem + DV, dP_mn + kk * 128, dO_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < BQ / 16; ++kk)   // dK += dS^T Q_i
-            umma_bf16(tmem + DK, dE_k + (kk >> 2) * 1024 + 2 * (kk & 3), dQ_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
+            umma_bf16(tmem + DK, dE_mn + kk * 128, dQ_(s) + kk * 128, idesc_a, (it > 0 || kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 128 / 16; ++kk)  // dQ_i = dS K      (contraction over the 128 keys of this CTA)
-            umma_bf16(tmem + DQ, dE_mn + kk * 128, dK_k + kk * 128, idesc_q, kk > 0);
+          for (int kk = 0; kk < 128 / 16; ++kk)  // dQ_i = dS K      (contraction over the 128 keys of this CTA; dS read K-major)
+            umma_bf16(tmem + DQ, dE_k + (kk >> 2) * 1024 + 2 * (kk & 3), dK_k + kk * 128, idesc_q, kk > 0);
           umma_commit(st_empty(s));
           umma_commit(acc_done);
           if (it + 1 == niter) umma_commit(kv_free);
@@ -250,34 +252,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float sl2 = scale * LOG2E_F;
-    // Column statistics (lse_i, delta_i) of this group's query columns live in a warp-private, double-buffered shared array:
-    // the first COLS/4 lanes fetch four lse values each, the next COLS/4 lanes four delta values, so the row warps never meet
-    // at a CTA barrier. The loads are unconditional (clamped index) and nothing touches their results until they are deposited
-    // one iteration later: a select or multiply right behind the load would stall the warp for the full DRAM latency.
-    constexpr int NL = COLS / 4;
-    float* wstat = stat + (warp - 4) * 2 * (2 * COLS);
-    const bool stat_lane = lane < 2 * NL;
-    const float* stat_src = (lane < NL) ? lse : delta;
-    const int sc0 = grp * COLS + (lane % NL) * 4;   // first of this lane's four columns inside the query block
-    auto stat_base = [&](int b, int h) { return stat_src + (static_cast<long long>(b) * H + h) * L; };
-    auto fetch_stat = [&](const float* base, int it, float (&v)[4]) {
-      if (stat_lane) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(base + min(it * BQ + sc0 + j, L - 1));
-      }
-    };
-    auto deposit_stat = [&](uint32_t g, int it, const float (&v)[4]) {   // lse * log2(e), +inf past the end (p == 0); delta, 0 past the end
-      if (stat_lane) {
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool in = it * BQ + sc0 + j < L;
-          o[j] = (lane < NL) ? (in ? v[j] * LOG2E_F : INFINITY) : (in ? v[j] : 0.f);
-        }
-        *reinterpret_cast<float4*>(wstat + (g & 1) * (2 * COLS) + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);   // delta lanes land in [COLS, 2 COLS)
-      }
-    };
-
+    // Row statistics: a thread owns query row `row` of every block, so lse and delta of that row are two scalars. They are
+    // loaded one block ahead with a clamped index, and nothing touches the loaded values until the next iteration starts
+    // (a select or multiply right behind the load would stall the warp for the full DRAM latency).
+    auto stat_ptr = [&](const float* src, int b, int h, int it) { return src + (static_cast<long long>(b) * H + h) * L + min(it * BQ + row, L - 1); };
     // this warp's 32 rows x DQC columns of a finished dQ tile. stage: TMEM -> registers -> staging box; issue (after a proxy
     // fence + __syncwarp by the caller): one bulk reduction into the global accumulator
     const uint32_t my_box = sDQ + (warp - 4) * (32 * DQC * 4);
@@ -303,38 +281,33 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     };
 
     uint32_t gi = 0;
+    float nxt_lse = 0.f, nxt_delta = 0.f;
     if (static_cast<int>(blockIdx.x) < total) {
       int b, h, r0;
       decode(blockIdx.x, b, h, r0);
-      float v[4];
-      fetch_stat(stat_base(b, h), 0, v);
-      deposit_stat(0, 0, v);
+      nxt_lse = __ldg(stat_ptr(lse, b, h, 0));
+      nxt_delta = __ldg(stat_ptr(delta, b, h, 0));
     }
-    __syncwarp();
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       int b, h, r0;
       decode(w, b, h, r0);
       const int g_row = r0 + row;
-      const uint32_t drop_base = static_cast<uint32_t>(g_row >> 1) * DROP_CK + drop.seed_lo;
       FB_TRACE_ITEM((w - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x));
-      const float* cur_stat = stat_base(b, h);
-      const float* nxt_item_stat = cur_stat;
       const bool more_items = w + static_cast<int>(gridDim.x) < total;
-      if (more_items) {
-        int nb, nh, nr0;
-        decode(w + gridDim.x, nb, nh, nr0);
-        nxt_item_stat = stat_base(nb, nh);
-      }
+      int nb = b, nh = h, nr0 = r0;
+      if (more_items) decode(w + gridDim.x, nb, nh, nr0);
       for (int it = 0; it < niter; ++it, ++gi) {
-        // statistics of the next query block (of this item, or the first block of the next item)
-        float nxt_stat[4] = {0.f, 0.f, 0.f, 0.f};
+        // this block's row statistics (loaded an iteration ago), then the request for the next block's
+        const uint32_t drop_base = static_cast<uint32_t>((b * H + h) * L + it * BQ + row) * DROP_CQ + drop.seed_lo;
+        const bool in_range = it * BQ + row < L;
+        const float lse_row = in_range ? nxt_lse * LOG2E_F : INFINITY;   // +inf past the end of the sequence: p == 0
+        const float delta_row = in_range ? nxt_delta : 0.f;
         const bool last = it + 1 == niter;
-        const bool has_next = !last || more_items;
-        const int nit = last ? 0 : it + 1;
-        if (has_next) fetch_stat(last ? nxt_item_stat : cur_stat, nit, nxt_stat);
+        if (!last || more_items) {
+          nxt_lse = __ldg(stat_ptr(lse, last ? nb : b, last ? nh : h, last ? 0 : it + 1));
+          nxt_delta = __ldg(stat_ptr(delta, last ? nb : b, last ? nh : h, last ? 0 : it + 1));
+        }
         ATT_STAMP_T(0, it, 0, 128);
-        const float* st_lse = wstat + (gi & 1) * (2 * COLS);
-        const float* st_delta = st_lse + COLS;
         ATT_STAMP_T(0, it, 1, 128);
         mbar_wait(t_full, gi & 1);
         tc_fence_after();
@@ -351,34 +324,22 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c * 32 + 4 * i4);
-            const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c * 32 + 4 * i4);
-            const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-            float pv[4];
-            if (i4 < VMAE_FB_POLY) {   // MUFU delivers 16 ex2/clk/SM: a share of the exponentials goes to the FMA pipe
-              fb_exp2_poly2(fmaf(__uint_as_float(ts[c][4 * i4]), sl2, -lv[0]), fmaf(__uint_as_float(ts[c][4 * i4 + 1]), sl2, -lv[1]), pv[0], pv[1]);
-              fb_exp2_poly2(fmaf(__uint_as_float(ts[c][4 * i4 + 2]), sl2, -lv[2]), fmaf(__uint_as_float(ts[c][4 * i4 + 3]), sl2, -lv[3]), pv[2], pv[3]);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) pv[t] = fb_ex2(fmaf(__uint_as_float(ts[c][4 * i4 + t]), sl2, -lv[t]));
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fb_ex2(fmaf(__uint_as_float(ts[c][i]), sl2, -lse_row));
+            const float p1 = fb_ex2(fmaf(__uint_as_float(ts[c][i + 1]), sl2, -lse_row));
+            float dp0 = __uint_as_float(tp[c][i]), dp1 = __uint_as_float(tp[c][i + 1]);
+            float pd0 = p0, pd1 = p1;   // the dropped probabilities (scaled by 1/(1-p) when dV is written out)
+            if (DROP) {   // same keep mask as the forward kernel: this thread owns query row `row`, the key pair varies
+              const int col = r0 + grp * COLS + c * 32 + i;   // global key index (even)
+              const uint32_t wd = drop_mix32(drop_base + static_cast<uint32_t>(col >> 1) * DROP_CK) ^ drop.seed_hi;
+              const bool d0 = (wd & 0xffffu) < drop.thr, d1 = (wd >> 16) < drop.thr;
+              dp0 = d0 ? 0.f : dp0 * drop.rp; pd0 = d0 ? 0.f : pd0;
+              dp1 = d1 ? 0.f : dp1 * drop.rp; pd1 = d1 ? 0.f : pd1;
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int i = 4 * i4 + t;
-              float dp = __uint_as_float(tp[c][i]);
-              float pd = pv[t];   // the dropped probability (scaled by 1/(1-p) when dV is written out)
-              if (DROP) {   // same keep mask as the forward kernel: hash of (seed, query row, key pair); this thread owns key g_row
-                const uint32_t rid = static_cast<uint32_t>((b * H + h) * L + it * BQ + grp * COLS + c * 32 + i);
-                const uint32_t wd = drop_mix32(rid * DROP_CQ + drop_base) ^ drop.seed_hi;
-                const bool dropped = (((g_row & 1) ? (wd >> 16) : (wd & 0xffffu)) < drop.thr);
-                dp = dropped ? 0.f : dp * drop.rp;
-                pd = dropped ? 0.f : pd;
-              }
-              ts[c][i] = __float_as_uint(pd);
-              tp[c][i] = __float_as_uint(pv[t] * (dp - dv[t]));
-            }
+            ts[c][i] = __float_as_uint(pd0);
+            ts[c][i + 1] = __float_as_uint(pd1);
+            tp[c][i] = __float_as_uint(p0 * (dp0 - delta_row));
+            tp[c][i + 1] = __float_as_uint(p1 * (dp1 - delta_row));
           }
         ATT_STAMP_T(0, it, 3, 128);
         if (it > 0) {
@@ -389,37 +350,31 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
           stage_dq();   // its bulk reduction is issued behind the proxy fence that also publishes dS^T below
           ATT_STAMP_T(0, it, 5, 128);
         }
-        // P^T columns -> TMEM operand (packed pairs), dS^T columns -> shared-memory tile (64-column SW128 chunks)
+        // P and dS columns of this query row -> the two [q x kv] shared-memory tiles (64-key SW128 chunks)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          uint32_t u[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = fb_pack(__uint_as_float(ts[c][2 * i]), __uint_as_float(ts[c][2 * i + 1]));
-          tmem_st16(tmem + TP + lane_off + grp * (COLS / 2) + c * 16, u);
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = grp * COLS + c * 32;   // first of these 32 query columns inside the block
-          const uint32_t row_base = sE + (col >> 6) * TILE + row * 128;
+          const int col = grp * COLS + c * 32;   // first of these 32 key columns inside the tile
+          const uint32_t off = (col >> 6) * TILE + row * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t addr = row_base + ((((col & 63) >> 3) + i) ^ (row & 7)) * 16;
-            fb_sts_u4(addr, fb_pack(__uint_as_float(tp[c][8 * i]), __uint_as_float(tp[c][8 * i + 1])),
+            const uint32_t sw = ((((col & 63) >> 3) + i) ^ (row & 7)) * 16;
+            fb_sts_u4(sP + off + sw, fb_pack(__uint_as_float(ts[c][8 * i]), __uint_as_float(ts[c][8 * i + 1])),
+                      fb_pack(__uint_as_float(ts[c][8 * i + 2]), __uint_as_float(ts[c][8 * i + 3])),
+                      fb_pack(__uint_as_float(ts[c][8 * i + 4]), __uint_as_float(ts[c][8 * i + 5])),
+                      fb_pack(__uint_as_float(ts[c][8 * i + 6]), __uint_as_float(ts[c][8 * i + 7])));
+            fb_sts_u4(sE + off + sw, fb_pack(__uint_as_float(tp[c][8 * i]), __uint_as_float(tp[c][8 * i + 1])),
                       fb_pack(__uint_as_float(tp[c][8 * i + 2]), __uint_as_float(tp[c][8 * i + 3])),
                       fb_pack(__uint_as_float(tp[c][8 * i + 4]), __uint_as_float(tp[c][8 * i + 5])),
                       fb_pack(__uint_as_float(tp[c][8 * i + 6]), __uint_as_float(tp[c][8 * i + 7])));
           }
         }
         ATT_STAMP_T(0, it, 6, 128);
-        tmem_wait_st();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
         if (it > 0) issue_dq(b, h, it - 1);
         ATT_STAMP_T(0, it, 7, 128);
-        if (has_next) deposit_stat(gi + 1, nit, nxt_stat);   // the other buffer: this warp finished reading it an iteration ago
-        __syncwarp();
       }
       // item tail: last dQ tile, then the dK / dV accumulators of this key tile (the producer is already loading the next K / V)
       ATT_STAMP_T(0, niter, 0, 128);
