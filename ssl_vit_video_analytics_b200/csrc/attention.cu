@@ -364,33 +364,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ======================================================================================================================
 // backward: delta = rowsum(dO * O), then one templated kernel in two modes.
 // ======================================================================================================================
+// HD/8 consecutive lanes share one (row, head): every lane reads one 16-byte piece of O and of dO, so a warp's loads are
+// fully coalesced (one thread per row-head would use 16 bytes of every 128-byte line per load instruction).
 template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                          float* __restrict__ delta, int B, int L, int H) {
   pdl_wait();
   pdl_launch_dependents();
-  const long long total = static_cast<long long>(B) * L * H;
+  constexpr int LPR = HD / 8;   // lanes per (row, head): 8 or 4
+  const long long total = static_cast<long long>(B) * L * H * LPR;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int hh = static_cast<int>(idx % H);
-    const long long bl = idx / H;
-    const int ll = static_cast<int>(bl % L);
-    const int bb = static_cast<int>(bl / L);
-    const uint4* po = reinterpret_cast<const uint4*>(o + idx * HD);
-    const uint4* pd = reinterpret_cast<const uint4*>(dout + idx * HD);
+  const long long total_pad = (total + 31) & ~31LL;   // whole warps stay in the loop: the shuffles below need every lane
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total_pad; t += stride) {
     float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+    if (t < total) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(o) + t), d = __ldg(reinterpret_cast<const uint4*>(dout) + t);
       const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
       const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&d);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 fa = __bfloat1622float2(a2[t]), fd = __bfloat1622float2(d2[t]);
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __bfloat1622float2(a2[k]), fd = __bfloat1622float2(d2[k]);
         acc += fa.x * fd.x + fa.y * fd.y;
       }
     }
-    delta[(static_cast<long long>(bb) * H + hh) * L + ll] = acc;
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (t < total && (t % LPR) == 0) {
+      const long long idx = t / LPR;   // (b, l, h) flattened, h fastest
+      const int hh = static_cast<int>(idx % H);
+      const long long bl = idx / H;
+      const int ll = static_cast<int>(bl % L);
+      const int bb = static_cast<int>(bl / L);
+      delta[(static_cast<long long>(bb) * H + hh) * L + ll] = acc;
+    }
   }
 }
 
@@ -812,9 +818,11 @@ extern "C" int vmae_attn_bwd(const void* qkv, const void* out, const void* dout,
   VMAE_CHECK_ARG(B > 0 && L > 0 && H > 0, "vmae_attn_bwd: bad shape B=%d L=%d H=%d", B, L, H);
   VMAE_CHECK_ARG(B <= 65535 && H <= 65535, "vmae_attn_bwd: B and H must be <= 65535");
   cudaStream_t s = (cudaStream_t)stream;
-  const long long total = (long long)B * L * H;
-  int grid = (int)((total + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  // delta: hd/8 lanes per (row, head), two 16-byte loads per thread; enough CTAs that one pass (or a few) covers everything
+  const long long total = (long long)B * L * H * (hd / 8);
+  long long grid_ll = (total + 255) / 256;
+  if (grid_ll > (long long)num_sms() * 128) grid_ll = (long long)num_sms() * 128;
+  const int grid = (int)grid_ll;
   int rc;
   if (hd == 64) {
     VMAE_CUDA(launch_pdl(PDL_ATTN, attn_delta_kernel<64>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, L, H));

@@ -27,11 +27,15 @@ static inline int mo_grid(long long rows) {
 // K4 forward. One warp per token. The token's pixels are staged in shared memory in prediction order (dt,py,px,c)
 // so that both the strided pixel reads (ps-float segments) and the pred/diff accesses are coalesced.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename PT>
+constexpr int MO_PF = 6;   // prediction chunks (256 elements each) requested ahead of the pixel gather: a 1536-wide token row
+// CPS / CPT: compile-time patch size / tubelet depth (0 = use the run-time arguments). The index arithmetic of the gather is
+// four divisions per load; with run-time divisors they were most of the kernel's instructions.
+template <typename PT, int CPS, int CPT>
 __global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_kernel(const float* __restrict__ clip, const PT* __restrict__ pred,
                                                                     const unsigned char* __restrict__ mask, float* __restrict__ acc,
-                                                                    __nv_bfloat16* __restrict__ diff, int B, int T, int H, int W, int pt,
-                                                                    int ps, int norm_pix) {
+                                                                    __nv_bfloat16* __restrict__ diff, int B, int T, int H, int W, int pt_arg,
+                                                                    int ps_arg, int norm_pix) {
+  const int ps = CPS ? CPS : ps_arg, pt = CPT ? CPT : pt_arg;
   extern __shared__ float tok_smem[];  // [MO_WARPS][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Tp = T / pt, hp = H / ps, wp = W / ps;
@@ -55,6 +59,16 @@ __global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_kernel(const float*
     const int w0 = n % wp; n /= wp;
     const int h0 = n % hp;
     const int t0 = n / hp;
+    // the token's prediction row does not depend on the pixel gather: request its first MO_PF chunks now, so that both
+    // streams are in flight together (a warp works through its tokens one after the other)
+    uint4 pf[MO_PF];
+    if constexpr (sizeof(PT) == 2) {
+#pragma unroll
+      for (int k = 0; k < MO_PF; ++k) {
+        const int e = lane * 8 + k * 256;
+        if (e < D) pf[k] = __ldg(reinterpret_cast<const uint4*>(pred + tok * D + e));
+      }
+    }
     // gather pixels: source order (c, dt, py, px), px fastest; one 16-byte load covers 4 consecutive px (ps % 4 == 0)
     float s = 0.f;
     for (int e = lane * 4; e < D; e += 128) {
@@ -82,10 +96,10 @@ __global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_kernel(const float*
       inv_std = rsqrtf(var + 1e-6f);
     }
     float sq = 0.f;
-    for (int e = lane * 8; e < D; e += 256) {
+    auto chunk = [&](const int e, const uint4 u_pre, const bool have_pre) {
       float pv[8];
       if constexpr (sizeof(PT) == 2) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(pred + tok * D + e));
+        const uint4 u = have_pre ? u_pre : __ldg(reinterpret_cast<const uint4*>(pred + tok * D + e));
         const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -111,8 +125,117 @@ __global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_kernel(const float*
         u.z = *reinterpret_cast<uint32_t*>(&a2); u.w = *reinterpret_cast<uint32_t*>(&a3);
         *reinterpret_cast<uint4*>(diff + tok * D + e) = u;
       }
+    };
+    if constexpr (sizeof(PT) == 2) {
+#pragma unroll
+      for (int k = 0; k < MO_PF; ++k) {
+        const int e = lane * 8 + k * 256;
+        if (e < D) chunk(e, pf[k], true);
+      }
+      for (int e = lane * 8 + MO_PF * 256; e < D; e += 256) chunk(e, make_uint4(0, 0, 0, 0), false);
+    } else {
+      for (int e = lane * 8; e < D; e += 256) chunk(e, make_uint4(0, 0, 0, 0), false);
     }
     __syncwarp();
+    loss_acc += warp_sum_f(sq) / (float)D;
+    cnt_acc += 1.f;
+  }
+  __shared__ float red[2][MO_WARPS];
+  if (lane == 0) { red[0][warp] = loss_acc; red[1][warp] = cnt_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < MO_WARPS; ++w) { a += red[0][w]; c += red[1][w]; }
+    if (c > 0.f) { atomicAdd(acc, a); atomicAdd(acc + 1, c); }
+  }
+}
+
+// The VideoMAE tubelet (2 x 16 x 16 pixels x 3 channels, D = 1536, bf16 predictions) without shared memory: a lane loads the
+// same four pixels of all three channels, which are 12 CONSECUTIVE elements of the prediction-ordered row (dt, py, px, c), so
+// the channel interleave happens in registers. All 48 pixel values and the 48 predictions of a lane are requested before
+// anything is consumed (a warp walks its tokens one after the other: memory-level parallelism has to come from inside a token).
+__global__ void __launch_bounds__(MO_THREADS) masked_mse_fwd_p16t2_kernel(const float* __restrict__ clip, const __nv_bfloat16* __restrict__ pred,
+                                                                          const unsigned char* __restrict__ mask, float* __restrict__ acc,
+                                                                          __nv_bfloat16* __restrict__ diff, int B, int T, int H, int W,
+                                                                          int norm_pix) {
+  constexpr int D = 1536, NIT = 4;   // 128 groups of 12 elements, 32 lanes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Tp = T / 2, hp = H / 16, wp = W / 16;
+  const int N = Tp * hp * wp;
+  const long long plane = (long long)H * W, chan = (long long)T * plane;
+  const long long total = (long long)B * N;
+  const long long wstride = (long long)gridDim.x * MO_WARPS;
+  float loss_acc = 0.f, cnt_acc = 0.f;
+  for (long long tok = (long long)blockIdx.x * MO_WARPS + warp; tok < total; tok += wstride) {
+    if (mask[tok] == 0) {
+      if (diff) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int e = lane * 8; e < D; e += 256) *reinterpret_cast<uint4*>(diff + tok * D + e) = z;
+      }
+      continue;
+    }
+    const int b = (int)(tok / N);
+    int n = (int)(tok % N);
+    const int w0 = n % wp; n /= wp;
+    const int h0 = n % hp;
+    const int t0 = n / hp;
+    const float* base = clip + (long long)b * 3 * chan + (long long)(t0 * 2) * plane + (long long)(h0 * 16) * W + w0 * 16;
+    const uint2* prow = reinterpret_cast<const uint2*>(pred + tok * D);
+    float x[NIT][12];
+    uint2 pu[NIT][3];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int g = it * 32 + lane;   // group: (dt, py, px / 4)
+      const long long off = (long long)(g >> 6) * plane + (long long)((g >> 2) & 15) * W + (g & 3) * 4;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + c * chan + off));
+        x[it][c] = v.x; x[it][3 + c] = v.y; x[it][6 + c] = v.z; x[it][9 + c] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pu[it][k] = __ldg(prow + g * 3 + k);
+    }
+    float mean = 0.f, inv_std = 1.f;
+    if (norm_pix) {
+      float s = 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s += x[it][i];
+      mean = warp_sum_f(s) / (float)D;
+      float q = 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const float a = x[it][i] - mean;
+          q += a * a;
+        }
+      const float var = warp_sum_f(q) / (float)(norm_pix == 1 ? D - 1 : D);
+      inv_std = rsqrtf(var + 1e-6f);
+    }
+    float sq = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int g = it * 32 + lane;
+      uint2 out[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pu[it][k]);
+        const float2 f0 = __bfloat1622float2(p2[0]), f1 = __bfloat1622float2(p2[1]);
+        const float d0 = f0.x - (x[it][4 * k] - mean) * inv_std, d1 = f0.y - (x[it][4 * k + 1] - mean) * inv_std;
+        const float d2 = f1.x - (x[it][4 * k + 2] - mean) * inv_std, d3 = f1.y - (x[it][4 * k + 3] - mean) * inv_std;
+        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(d0, d1), a1 = __floats2bfloat162_rn(d2, d3);
+        out[k].x = *reinterpret_cast<uint32_t*>(&a0);
+        out[k].y = *reinterpret_cast<uint32_t*>(&a1);
+      }
+      if (diff) {
+        uint2* drow = reinterpret_cast<uint2*>(diff + tok * D);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) drow[g * 3 + k] = out[k];
+      }
+    }
     loss_acc += warp_sum_f(sq) / (float)D;
     cnt_acc += 1.f;
   }
@@ -512,12 +635,14 @@ extern "C" int vmae_masked_mse_fwd(const float* clip, const void* pred, int pred
   const long long total = (long long)B * (T / pt) * (H / ps) * (W / ps);
   const int grid = mo_grid(total);
   cudaStream_t s = (cudaStream_t)stream;
-  if (pred_dtype == VMAE_DTYPE_BF16) {
-    auto k = masked_mse_fwd_kernel<__nv_bfloat16>;
+  if (pred_dtype == VMAE_DTYPE_BF16 && ps == 16 && pt == 2 && W % 4 == 0) {   // the VideoMAE tubelet: register-only kernel
+    masked_mse_fwd_p16t2_kernel<<<grid, MO_THREADS, 0, s>>>(clip, (const __nv_bfloat16*)pred, mask, acc, (__nv_bfloat16*)diff, B, T, H, W, norm_pix);
+  } else if (pred_dtype == VMAE_DTYPE_BF16) {
+    auto k = masked_mse_fwd_kernel<__nv_bfloat16, 0, 0>;
     if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, MO_THREADS, smem, s>>>(clip, (const __nv_bfloat16*)pred, mask, acc, (__nv_bfloat16*)diff, B, T, H, W, pt, ps, norm_pix);
   } else if (pred_dtype == VMAE_DTYPE_F32) {
-    auto k = masked_mse_fwd_kernel<float>;
+    auto k = masked_mse_fwd_kernel<float, 0, 0>;
     if (smem > 40 * 1024) VMAE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, MO_THREADS, smem, s>>>(clip, (const float*)pred, mask, acc, (__nv_bfloat16*)diff, B, T, H, W, pt, ps, norm_pix);
   } else {

@@ -141,7 +141,8 @@ def test_attention_rejects_unsupported_head_dim(env):
         ops.attn_fwd(qkv, 1, 16, 1, 48)
 
 
-@pytest.mark.parametrize("B,T,S,pt,ps,norm", [(2, 8, 112, 1, 8, 1), (2, 4, 64, 2, 16, 1), (1, 2, 32, 1, 8, 2), (1, 2, 32, 1, 8, 0)])
+@pytest.mark.parametrize("B,T,S,pt,ps,norm", [(2, 8, 112, 1, 8, 1), (2, 4, 64, 2, 16, 1), (1, 2, 32, 1, 8, 2), (1, 2, 32, 1, 8, 0),
+                                                  (3, 6, 80, 2, 16, 0), (2, 2, 48, 2, 16, 2)])
 def test_masked_mse_matches_reference_formula(env, B, T, S, pt, ps, norm):
     from oracle import restatement as R
 
