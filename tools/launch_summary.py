@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: total time and share per kernel (template arguments kept).
-usage: python tools/launch_summary.py launches.csv [header comment ...] > profiles/rN_bench_launch_summary.txt"""
+usage: python tools/launch_summary.py launches.csv [--one-step] [header comment ...] > profiles/rN_bench_launch_summary.txt"""
 import csv
 import re
 import sys
@@ -21,6 +21,19 @@ for r in rd:
     name = r[ci["Kernel Name"]]
     name = re.sub(r"\(.*$", "", name).replace("void ", "")
     rows.append((name, us))
+if "--one-step" in sys.argv:
+    # the launch list covers several training steps: find the period of the kernel-name sequence and keep exactly one step
+    sys.argv.remove("--one-step")
+    names = [n for n, _ in rows]
+    period = None
+    for P in range(50, len(names) // 2):
+        if all(names[i] == names[i + P] for i in range(len(names) - P)):
+            period = P
+            break
+    if period is None:
+        raise SystemExit("no periodic step structure found in the launch list")
+    rows = rows[:period]
+    sys.argv.append(f"exactly one step: {period} launches (period of the kernel-name sequence over {len(names)} captured launches)")
 tot = sum(u for _, u in rows)
 agg = defaultdict(lambda: [0.0, 0])
 for n, u in rows:
