@@ -175,6 +175,13 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    if use_graph:
+        # everything runs on a non-default stream from the start: autograd binds each gradient accumulator to the stream it first
+        # saw, and a capture may not synchronise with the legacy default stream
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the capture stream differs by design
     torch.manual_seed(0)
     if args.workload == "tinyvit":
         # the drop-in TinyVideoMAE at the reference's own configs/ssl_mae.yaml shapes (reported next to the headline)
@@ -213,18 +220,40 @@ def run_ours(args, cfg):
 
         def loss_fn(clip):
             return model.training_loss(clip, mask_d, vis_d)
-    opt = torch.optim.AdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05, fused=True)
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05, fused=True, capturable=use_graph)
     clip_pinned = [clip_h.pin_memory(), clip_h.clone().pin_memory()]
     clip_d = clip_h.to(dev)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
-    def step(clip):
+    def eager_step(clip):
         ddp.zero_grad()
         loss = loss_fn(clip)
         loss.backward()
         ddp.finish_gradient_sync()
         opt.step()
         return loss
+
+    # The whole step (zero-grad, forward, loss, backward, gradient sync, AdamW) is captured once per input buffer into a CUDA
+    # graph and replayed: ~400 launches per step cost the host 12 ms of the 18 ms a step takes on the GPU, which leaves no
+    # slack for the copy/readback bookkeeping of the e2e loop. The graphs share one memory pool (they never run concurrently
+    # and hand nothing to each other but parameters, gradients and optimizer state, which live outside the pool).
+    graphs = {}
+
+    def capture(clip):
+        g = torch.cuda.CUDAGraph()
+        pool = next(iter(graphs.values()))[0].pool() if graphs else None
+        ops.reset_launch_count()
+        with torch.cuda.graph(g, pool=pool):
+            out = eager_step(clip)
+        graphs[clip.data_ptr()] = (g, out, ops.launch_count())
+
+    def step(clip):
+        if not use_graph:
+            return eager_step(clip)
+        g, out, n = graphs[clip.data_ptr()]
+        g.replay()
+        ops.add_launch_count(n)
+        return out
 
     def barrier():
         if world > 1:
@@ -238,10 +267,20 @@ def run_ours(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up
+    # ---- warm-up (eager: also initialises everything a capture must not do for the first time), then the captures
     for _ in range(args.warmup):
-        loss = step(clip_d)
+        loss = eager_step(clip_d)
     barrier()
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(clip_d), torch.empty_like(clip_d)]
+    if use_graph:
+        bufs[0].copy_(clip_d)
+        bufs[1].copy_(clip_d)
+        for t in (clip_d, bufs[0], bufs[1]):
+            capture(t)
+        for _ in range(args.warmup):
+            loss = step(clip_d)
+        barrier()
 
     # ---- value: inputs resident in HBM (the 616 MB clip + ~20 GB of activations exceed the 126 MB L2 every step)
     sampler = ClockSampler(local)
@@ -258,12 +297,10 @@ def run_ours(args, cfg):
     launches = ops.launch_count()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- e2e: pinned-host clip -> device every step, loss read back every step; the copy of step i+1 is issued on a
     #      side stream while step i computes (the loader-prefetch pattern of train_ssl_mae.py:67 non_blocking copies)
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [torch.empty_like(clip_d), torch.empty_like(clip_d)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -300,6 +337,17 @@ def run_ours(args, cfg):
         last = float(loss_hosts[(n - 1) % 2])
         return last
 
+    # the H2D copy of one clip batch on its own (no compute): the floor the e2e step cannot go below
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        h0.record(copy_stream)
+        for i in range(4):
+            bufs[i % 2].copy_(clip_pinned[i % 2], non_blocking=True)
+        h1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_ms_alone = h0.elapsed_time(h1) / 4.0
+
     e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
@@ -313,7 +361,7 @@ def run_ours(args, cfg):
     # ---- roofline leg: the same step with CUDA events around every launch of ours (separate region: events perturb)
     ops.profile_start()
     for _ in range(2):
-        step(clip_d)
+        eager_step(clip_d)
     prof = ops.profile_stop()
     for v in prof.values():
         v["ms"] /= 2.0
@@ -354,10 +402,10 @@ def run_ours(args, cfg):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "AdamW(fused)",
-                   "final_loss": final_loss},
+                   "cuda_graph": use_graph, "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps, "note": "pinned fp32 clip batch copied H2D every step (double-buffered on a copy stream); the loss of every step is copied D2H to pinned memory and read by the host one step later, inside the timed region"},
+                "ms_per_step": e2e_ms / args.steps, "h2d_ms_alone": h2d_ms_alone, "note": "pinned fp32 clip batch copied H2D every step (double-buffered on a copy stream); the loss of every step is copied D2H to pinned memory and read by the host one step later, inside the timed region"},
         "gpu_launches": launches,
         "roofline": roofline,
     }
@@ -382,6 +430,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step from a CUDA graph (auto: on for one GPU, off under torchrun)")
     ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit"],
                     help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes")
     args = ap.parse_args()

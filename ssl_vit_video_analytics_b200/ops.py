@@ -30,6 +30,11 @@ def launch_count() -> int:
     return _launches
 
 
+def add_launch_count(n: int) -> None:
+    """A CUDA-graph replay launches the kernels that were counted while it was captured."""
+    _count(n)
+
+
 def _count(n: int = 1) -> None:
     global _launches
     _launches += n
