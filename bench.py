@@ -163,6 +163,7 @@ def run_ours(args, cfg):
     import torch.distributed as dist
 
     from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.graph_step import GraphedTrainStep, use_side_stream
     from ssl_vit_video_analytics_b200.models import VideoMAEViT
     from ssl_vit_video_analytics_b200.parallel import GradientBucketer
 
@@ -180,9 +181,7 @@ def run_ours(args, cfg):
     if use_graph:
         # everything runs on a non-default stream from the start: autograd binds each gradient accumulator to the stream it first
         # saw, and a capture may not synchronise with the legacy default stream
-        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
-        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the capture stream differs by design
+        use_side_stream(dev)
     torch.manual_seed(0)
     if args.workload == "tinyvit":
         # the drop-in TinyVideoMAE at the reference's own configs/ssl_mae.yaml shapes (reported next to the headline)
@@ -238,23 +237,10 @@ def run_ours(args, cfg):
     # graph and replayed: ~400 launches per step cost the host 12 ms of the 18 ms a step takes on the GPU, which leaves no
     # slack for the copy/readback bookkeeping of the e2e loop. The graphs share one memory pool (they never run concurrently
     # and hand nothing to each other but parameters, gradients and optimizer state, which live outside the pool).
-    graphs = {}
-
-    def capture(clip):
-        g = torch.cuda.CUDAGraph()
-        pool = next(iter(graphs.values()))[0].pool() if graphs else None
-        ops.reset_launch_count()
-        with torch.cuda.graph(g, pool=pool):
-            out = eager_step(clip)
-        graphs[clip.data_ptr()] = (g, out, ops.launch_count())
+    graphed = GraphedTrainStep(eager_step)
 
     def step(clip):
-        if not use_graph:
-            return eager_step(clip)
-        g, out, n = graphs[clip.data_ptr()]
-        g.replay()
-        ops.add_launch_count(n)
-        return out
+        return graphed.replay(clip) if use_graph else eager_step(clip)
 
     def barrier():
         if world > 1:
@@ -278,7 +264,7 @@ def run_ours(args, cfg):
         bufs[0].copy_(clip_d)
         bufs[1].copy_(clip_d)
         for t in (clip_d, bufs[0], bufs[1]):
-            capture(t)
+            graphed.capture(t)
         for _ in range(args.warmup):
             loss = step(clip_d)
         barrier()

@@ -280,3 +280,82 @@ def test_finetune_classifier_vs_oracle():
     with torch.no_grad():
         z0 = model.video_embedding(clip.cuda())
     assert z0.shape == (2, 576) and z0.dtype == torch.float32
+
+
+def test_graphed_train_step_matches_eager():
+    """graph_step.GraphedTrainStep: three replayed steps (two input buffers) leave the same parameters and losses as three
+    eager steps from the same start. Gradient buckets, AdamW state and the loss tensor are static; only the inputs change."""
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
+    from ssl_vit_video_analytics_b200.graph_step import GraphedTrainStep, use_side_stream
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+    from ssl_vit_video_analytics_b200.parallel import GradientBucketer
+
+    cfg = {"dataset": {"clip_len": 4, "image_size": 64},
+           "model": {"embed_dim": 384, "depth": 2, "num_heads": 6, "tubelet": [2, 16, 16], "decoder_embed_dim": 384, "decoder_depth": 1,
+                     "decoder_num_heads": 6, "decoder_dropout": 0.0},
+           "ssl": {"mask_ratio": 0.75, "norm_pix_loss": True}}
+    dev = torch.device("cuda:0")
+    prev = torch.cuda.current_stream(dev)
+    use_side_stream(dev)
+    try:
+        g = torch.Generator().manual_seed(5)
+        clips = [torch.randn(2, 3, 4, 64, 64, generator=g).to(dev) for _ in range(3)]
+        torch.manual_seed(6)
+        mask = get_tube_mask(2, 2, 16, 0.75)
+        mask_d, vis_d = mask.to(dev), visible_indices(mask).to(dev)
+
+        def run(graphed: bool):
+            torch.manual_seed(0)
+            model = VideoMAEViT(cfg).to(dev).train()
+            ddp = GradientBucketer(model, bucket_mb=1.0, exclude=())
+            opt = torch.optim.AdamW(list(model.parameters()), lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+
+            def step(clip):
+                ddp.zero_grad()
+                loss = model.training_loss(clip, mask_d, vis_d)
+                loss.backward()
+                ddp.finish_gradient_sync()
+                opt.step()
+                return loss
+
+            losses = []
+            if graphed:
+                bufs = [torch.zeros_like(clips[0]), torch.zeros_like(clips[0])]
+                snap = {k: v.clone() for k, v in model.state_dict().items()}
+                step(bufs[0])                                       # eager warm-up (creates the optimizer state), then back to the start
+                model.load_state_dict(snap)
+                for st in opt.state.values():                       # in place: the captured step must see the SAME state tensors
+                    st["exp_avg"].zero_()
+                    st["exp_avg_sq"].zero_()
+                    st["step"].zero_()
+                gs = GraphedTrainStep(step)
+                for b in bufs:
+                    gs.capture(b)                                  # a capture does not execute anything
+                assert gs.launches_per_step(bufs[0]) > 0
+                for i, c in enumerate(clips):
+                    bufs[i % 2].copy_(c)
+                    losses.append(float(gs.replay(bufs[i % 2]).detach()))
+                with pytest.raises(RuntimeError, match="not captured"):
+                    gs.replay(clips[0])
+            else:
+                for c in clips:
+                    losses.append(float(step(c).detach()))
+            torch.cuda.synchronize()
+            return losses, {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+
+        def dist(a, b):
+            num = sum(float(((a[k] - b[k]) ** 2).sum()) for k in a)
+            den = sum(float((a[k] ** 2).sum()) for k in a)
+            return (num / den) ** 0.5
+
+        l_e, sd_e = run(False)
+        l_e2, sd_e2 = run(False)
+        l_g, sd_g = run(True)
+        for a, b in zip(l_e, l_g):
+            assert abs(a - b) <= 2e-3 * abs(a), (l_e, l_g)
+        # Two eager runs already differ (fp32 atomics in the split-K weight gradients, amplified by Adam's sign-like first
+        # steps): the graphed run has to stay within that noise floor of the eager one.
+        floor = dist(sd_e, sd_e2)
+        assert dist(sd_e, sd_g) <= 3.0 * floor + 1e-4, (dist(sd_e, sd_g), floor)
+    finally:
+        torch.cuda.set_stream(prev)
