@@ -176,8 +176,7 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # one GPU only: capturing the bucketed NCCL allreduce (side stream + post-accumulate hooks) deadlocked on 2 GPUs when tried
-    use_graph = args.graph != "off" and world == 1
+    use_graph = args.graph != "off"
     if use_graph:
         # everything runs on a non-default stream from the start: autograd binds each gradient accumulator to the stream it first
         # saw, and a capture may not synchronise with the legacy default stream
@@ -237,10 +236,28 @@ def run_ours(args, cfg):
     # graph and replayed: ~400 launches per step cost the host 12 ms of the 18 ms a step takes on the GPU, which leaves no
     # slack for the copy/readback bookkeeping of the e2e loop. The graphs share one memory pool (they never run concurrently
     # and hand nothing to each other but parameters, gradients and optimizer state, which live outside the pool).
-    graphed = GraphedTrainStep(eager_step)
+    # N > 1: the NCCL collectives stay outside the graphs (capturing the hook-driven bucket allreduce deadlocked when tried):
+    # graph 1 = zero-grad + forward + loss + backward into the gradient buckets, then the bucket allreduces eagerly on the same
+    # stream, then graph 2 = AdamW. The allreduce (119 MB over NVLink) is no longer hidden behind backward; what it costs is
+    # less than what the host-side launch work cost.
+    def fwd_bwd(clip):
+        ddp.zero_grad()
+        loss = loss_fn(clip)
+        loss.backward()
+        ddp.finish_gradient_sync()
+        return loss
+
+    graphed = GraphedTrainStep(eager_step if world == 1 else fwd_bwd)
+    opt_graph = torch.cuda.CUDAGraph() if (use_graph and world > 1) else None
 
     def step(clip):
-        return graphed.replay(clip) if use_graph else eager_step(clip)
+        if not use_graph:
+            return eager_step(clip)
+        loss = graphed.replay(clip)
+        if world > 1:
+            ddp.allreduce_now()
+            opt_graph.replay()
+        return loss
 
     def barrier():
         if world > 1:
@@ -263,8 +280,12 @@ def run_ours(args, cfg):
     if use_graph:
         bufs[0].copy_(clip_d)
         bufs[1].copy_(clip_d)
+        ddp.defer_comm = world > 1
         for t in (clip_d, bufs[0], bufs[1]):
             graphed.capture(t)
+        if opt_graph is not None:
+            with torch.cuda.graph(opt_graph, pool=graphed.pool()):
+                opt.step()
         for _ in range(args.warmup):
             loss = step(clip_d)
         barrier()
@@ -346,6 +367,7 @@ def run_ours(args, cfg):
     _ = time.perf_counter() - t0
 
     # ---- roofline leg: the same step with CUDA events around every launch of ours (separate region: events perturb)
+    ddp.defer_comm = False
     ops.profile_start()
     for _ in range(2):
         eager_step(clip_d)
@@ -389,7 +411,7 @@ def run_ours(args, cfg):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "AdamW(fused)",
-                   "cuda_graph": use_graph, "final_loss": final_loss},
+                   "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else ("after backward, between two graphs" if use_graph else "bucketed, overlapped with backward")), "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps, "h2d_ms_alone": h2d_ms_alone, "note": "pinned fp32 clip batch copied H2D every step (double-buffered on a copy stream); the loss of every step is copied D2H to pinned memory and read by the host one step later, inside the timed region"},
@@ -418,7 +440,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the training step from a CUDA graph (one GPU only; under torchrun the step always runs eagerly)")
+                    help="replay the training step from CUDA graphs (default on; under torchrun the NCCL allreduce runs between two graphs)")
     ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit"],
                     help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes")
     args = ap.parse_args()

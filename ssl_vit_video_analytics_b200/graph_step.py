@@ -11,7 +11,8 @@ Rules the caller has to follow (they are the usual ones of `torch.cuda.graph`):
   * the optimizer must be built with `capturable=True`, and its state must exist before the capture (run at least one eager
     step with the same optimizer object first): state created inside a capture is re-initialised by every replay;
   * inputs are static buffers: copy each batch into one of the buffers that were captured, then `replay(buffer)`;
-  * single process only — capturing the bucketed NCCL allreduce of `parallel.GradientBucketer` is not supported.
+  * collectives stay outside the graph: with `parallel.GradientBucketer` set `defer_comm = True`, capture forward+backward,
+    call `allreduce_now()` eagerly after each replay and run (or separately capture) the optimizer step after it.
 """
 from __future__ import annotations
 
@@ -62,6 +63,10 @@ class GraphedTrainStep:
         g.replay()
         ops.add_launch_count(n)   # a replay launches the kernels that were counted while it was captured
         return out
+
+    def pool(self):
+        """Memory pool of the captures (pass it to further `torch.cuda.graph(..., pool=...)` captures of the same step)."""
+        return next(iter(self._graphs.values()))[0].pool() if self._graphs else None
 
     def launches_per_step(self, buf: torch.Tensor) -> int:
         return self._graphs[buf.data_ptr()][2]

@@ -71,6 +71,10 @@ class GradientBucketer(nn.Module):
                 p.register_post_accumulate_grad_hook(self._on_grad_ready)
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.on_cuda else None
         self.launched = 0
+        # defer_comm: backward only fills the buckets (nothing is sent from the hooks); the caller runs `allreduce_now()`
+        # afterwards. This is the mode for a forward+backward that is replayed from a CUDA graph (graph_step.py): the
+        # collectives stay outside the graph.
+        self.defer_comm = False
         if self.on_cuda:
             # fused blocks that accumulate straight into the bucket views report completion through this hook
             from . import ops
@@ -103,7 +107,7 @@ class GradientBucketer(nn.Module):
 
     def _launch(self, b: _Bucket):
         self.launched += 1
-        if self.world == 1:
+        if self.world == 1 or self.defer_comm:
             return
         if self.on_cuda:
             ev = torch.cuda.Event()
@@ -125,10 +129,21 @@ class GradientBucketer(nn.Module):
                 raise RuntimeError(f"a gradient bucket was not completed by backward: a parameter received no gradient "
                                    f"(missing {missing[:8]}); exclude parameters that never get a gradient via "
                                    f"GradientBucketer(exclude=...)")
-            if self.world == 1:
+            if self.world == 1 or self.defer_comm:
                 continue
             if self.on_cuda:
                 torch.cuda.current_stream(self.device).wait_event(b.event)
             else:
                 b.work.wait()
+                b.flat.div_(self.world)
+
+    def allreduce_now(self):
+        """Average every bucket across ranks on the current stream (the `defer_comm` counterpart of the hook-driven path)."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if self.on_cuda:
+                dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
                 b.flat.div_(self.world)

@@ -45,6 +45,17 @@ def _worker(rank, world, port, tmp):
         loss.backward()
         ddp.finish_gradient_sync()
     grads = [p.grad.clone() for p in model.parameters()]
+    # deferred communication (the CUDA-graph mode): backward only fills the buckets, allreduce_now() averages them
+    ddp.defer_comm = True
+    ddp.zero_grad()
+    ((ddp(xs) - ys) ** 2).mean().backward()
+    ddp.finish_gradient_sync()
+    local_only = [p.grad.clone() for p in model.parameters()]
+    ddp.allreduce_now()
+    for p, a in zip(model.parameters(), grads):
+        assert torch.allclose(p.grad, a, rtol=1e-6, atol=1e-8)
+    assert any(not torch.allclose(l, a, rtol=1e-3, atol=1e-6) for l, a in zip(local_only, grads))   # nothing was sent before
+    ddp.defer_comm = False
     # FedAvg: rank r plays client r with weight r + 1
     fmodel = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
     torch.manual_seed(100 + rank)
