@@ -12,8 +12,8 @@ Rules the caller has to follow (they are the usual ones of `torch.cuda.graph`):
     step with the same optimizer object first): state created inside a capture is re-initialised by every replay;
   * inputs are static buffers: copy each batch into one of the buffers that were captured, then `replay(buffer)`;
   * decoder dropout: the kernels take their seeds as host-side arguments (drawn from torch's CPU generator per call), so a
-    captured step would replay the SAME keep masks every iteration — capture only with `decoder_dropout = 0` (as the parity and
-    benchmark configurations do) or run eagerly;
+    captured step would replay the SAME keep masks every iteration — `ops.new_dropout_seeds` refuses to run under capture:
+    capture only with `decoder_dropout = 0` (as the parity and benchmark configurations do) or run eagerly;
   * collectives stay outside the graph: with `parallel.GradientBucketer` set `defer_comm = True`, capture forward+backward,
     call `allreduce_now()` eagerly after each replay and run (or separately capture) the optimizer step after it.
 """

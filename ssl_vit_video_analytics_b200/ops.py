@@ -349,6 +349,9 @@ def dropout_mask(n, p_drop, seed, device):
 
 def new_dropout_seeds(k):
     """k fresh 63-bit seeds from torch's CPU generator (deterministic under torch.manual_seed, no device sync)."""
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("dropout inside a CUDA-graph capture: the seeds are host-side kernel arguments, so every replay would reuse "
+                           "the same keep masks; capture with dropout 0 or run the step eagerly")
     return [int(v) for v in torch.randint(0, 2 ** 62, (k,), dtype=torch.int64).tolist()]
 
 
