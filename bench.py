@@ -165,6 +165,7 @@ def run_ours(args, cfg):
     from ssl_vit_video_analytics_b200 import ops
     from ssl_vit_video_analytics_b200.graph_step import GraphedTrainStep, use_side_stream
     from ssl_vit_video_analytics_b200.models import VideoMAEViT
+    from ssl_vit_video_analytics_b200.optim import FusedAdamW
     from ssl_vit_video_analytics_b200.parallel import GradientBucketer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +220,7 @@ def run_ours(args, cfg):
 
         def loss_fn(clip):
             return model.training_loss(clip, mask_d, vis_d)
-    opt = torch.optim.AdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05, fused=True, capturable=use_graph)
+    opt = FusedAdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05)   # row a18: one launch, device-side hyper-parameters
     clip_pinned = [clip_h.pin_memory(), clip_h.clone().pin_memory()]
     clip_d = clip_h.to(dev)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -457,7 +458,7 @@ def run_ours(args, cfg):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "AdamW(fused)",
+                   "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "optim.FusedAdamW (vmae_adamw_multi)",
                    "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else ("after backward, between two graphs" if use_graph else "bucketed, overlapped with backward")), "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,

@@ -193,6 +193,13 @@ int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
 /* fp32 master weights -> bf16 operand copies for a whole parameter set in one launch. `table` is a DEVICE array of
  * `count` entries {const float* src; bf16* dst; long long n;} (24 bytes each; src and dst 16-byte aligned). */
 int vmae_multi_cast_f32_to_bf16(const void* table, int count, void* stream);
+/* a18: AdamW with decoupled weight decay over many fp32 tensors in one launch (torch.optim.AdamW semantics,
+ * train_ssl_mae.py:163). table (device): `chunks` entries {float* p; const float* g; float* m; float* v; int64 n}, each at most
+ * vmae_adamw_chunk() elements of one tensor. hp (device, 6 floats): lr, beta1, beta2, eps, weight_decay, step; the call first
+ * increments step, then updates p, m, v in place with bias corrections 1 - beta^step. Nothing is read from the host at run
+ * time, so a captured call replays correctly after the host has changed hp[0] (learning-rate schedule). */
+int vmae_adamw_multi(const void* table, int chunks, float* hp, void* stream);
+int vmae_adamw_chunk(void);
 /* out = dy * dact (dact = the gelu' tensor saved by the GELU epilogue); bf16, n elements (n % 4 == 0) */
 int vmae_gelu_bwd(const void* dy, const void* dact, void* out, long long n, void* stream);
 /* db[n] += sum_m dy[m,n]   (bias gradient; dy bf16 or fp32 [M, ld]) */

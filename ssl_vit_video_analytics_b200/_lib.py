@@ -56,6 +56,8 @@ SIGNATURES = {
     "vmae_cast_f32_to_bf16": [_p, _p, _ll, _p],
     "vmae_cast_bf16_to_f32": [_p, _p, _ll, _p],
     "vmae_multi_cast_f32_to_bf16": [_p, _i, _p],
+    "vmae_adamw_multi": [_p, _i, _p, _p],
+    "vmae_adamw_chunk": [],
     "vmae_gelu_bwd": [_p, _p, _p, _ll, _p],
     "vmae_colsum_accum": [_p, _i, _ll, _p, _ll, _i, _p],
     "vmae_add_gaussian_noise": [_p, _p, _i, _p, _ll, _f, _ull, _ull, _p],

@@ -327,6 +327,50 @@ __global__ void __launch_bounds__(EW_THREADS) multi_cast_f32_bf16_kernel(const C
   for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += stride) e.dst[i] = __float2bfloat16_rn(e.src[i]);
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// AdamW over many tensors in one launch (train_ssl_mae.py:163: torch.optim.AdamW on every parameter, decoupled weight decay).
+// table: one entry per chunk of at most ADAMW_CHUNK elements of one tensor; hp (device): lr, beta1, beta2, eps,
+// weight_decay, step (float, already incremented for this update by adamw_tick_kernel). Everything the update depends on
+// lives on the device, so a captured step replays correctly while the host changes lr between replays.
+// ----------------------------------------------------------------------------------------------------------------------
+struct AdamWEntry {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+};
+constexpr int ADAMW_CHUNK = 16384;
+__global__ void adamw_tick_kernel(float* hp) { hp[5] += 1.0f; }
+__global__ void __launch_bounds__(EW_THREADS) adamw_multi_kernel(const AdamWEntry* __restrict__ table, const float* __restrict__ hp) {
+  const AdamWEntry e = table[blockIdx.x];
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], step = hp[5];
+  const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.0f - lr * wd;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    p *= decay;
+    m = b1 * m + (1.0f - b1) * g;            // torch: exp_avg.lerp_(grad, 1 - beta1)
+    v = b2 * v + (1.0f - b2) * g * g;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    p -= step_size * (m / denom);
+  };
+  const bool vec = (((uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v) & 15) == 0;
+  const long long n4 = vec ? e.n / 4 : 0;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(e.p)[i], m = reinterpret_cast<float4*>(e.m)[i], v = reinterpret_cast<float4*>(e.v)[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(e.g) + i);
+    upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+    reinterpret_cast<float4*>(e.p)[i] = p;
+    reinterpret_cast<float4*>(e.m)[i] = m;
+    reinterpret_cast<float4*>(e.v)[i] = v;
+  }
+  for (long long i = n4 * 4 + threadIdx.x; i < e.n; i += blockDim.x) {
+    float p = e.p[i], m = e.m[i], v = e.v[i];
+    upd(p, e.g[i], m, v);
+    e.p[i] = p; e.m[i] = m; e.v[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
   const long long n4 = n / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -568,6 +612,16 @@ extern "C" int vmae_multi_cast_f32_to_bf16(const void* table, int count, void* s
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
+extern "C" int vmae_adamw_multi(const void* table, int chunks, float* hp, void* stream) {
+  VMAE_CHECK_ARG(chunks >= 0 && hp && (chunks == 0 || table), "vmae_adamw_multi: bad args");
+  adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hp);
+  VMAE_LAUNCH_CHECK();
+  if (chunks == 0) return VMAE_OK;
+  adamw_multi_kernel<<<chunks, EW_THREADS, 0, (cudaStream_t)stream>>>((const AdamWEntry*)table, hp);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
+extern "C" int vmae_adamw_chunk(void) { return ADAMW_CHUNK; }
 extern "C" int vmae_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream) {
   VMAE_CHECK_ARG(n >= 0 && (n == 0 || (x && y)), "vmae_cast_bf16_to_f32: bad args");
   if (n == 0) return VMAE_OK;

@@ -26,14 +26,17 @@ from .masking import count_masked, count_visible, get_mask_ratio, make_token_mas
 
 
 def build_optimizer(cfg: Dict[str, Any], model: nn.Module) -> torch.optim.Optimizer:
-    """train_mae.py:45-50 (AdamW, betas default (0.9, 0.95), weight decay on every parameter); fused on CUDA parameters."""
+    """train_mae.py:45-50 (AdamW, betas default (0.9, 0.95), weight decay on every parameter); `optim.FusedAdamW` on CUDA parameters."""
     opt_cfg = cfg.get("optimizer", {})
     lr = float(opt_cfg.get("lr", opt_cfg.get("base_lr", 3e-4)))
     wd = float(opt_cfg.get("weight_decay", 0.05))
     betas = tuple(opt_cfg.get("betas", [0.9, 0.95]))
     params = list(model.parameters())
-    fused = len(params) > 0 and all(p.is_cuda for p in params)
-    return torch.optim.AdamW(params, lr=lr, weight_decay=wd, betas=betas, fused=fused)
+    if len(params) > 0 and all(p.is_cuda for p in params):
+        from ..optim import FusedAdamW   # one launch per group, device-side hyper-parameters (graph-capturable)
+
+        return FusedAdamW(params, lr=lr, weight_decay=wd, betas=betas)
+    return torch.optim.AdamW(params, lr=lr, weight_decay=wd, betas=betas)   # host-side logic tests run on CPU modules
 
 
 def build_scheduler(cfg: Dict[str, Any], optimizer: torch.optim.Optimizer):

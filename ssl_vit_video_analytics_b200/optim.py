@@ -1,0 +1,100 @@
+"""AdamW on the GPU in one launch (`torch.optim.AdamW(model.parameters(), lr, weight_decay)` at
+`src/train_ssl_mae.py:163`, `src/mae/engine.py` via `build_optimizer`).
+
+Same constructor arguments, `param_groups`, `state` and update rule as `torch.optim.AdamW` (decoupled weight decay, bias
+correction with the per-parameter step count); the difference is where things live: every hyper-parameter the update reads
+(lr, betas, eps, weight decay, step) sits in a small device array per parameter group, and all tensors of a group are updated by
+ONE kernel launch through a device-side chunk table (`vmae_adamw_multi`). Nothing is read from the host at run time, so a step
+captured in a CUDA graph (graph_step.py) stays correct while a scheduler changes `param_groups[i]["lr"]` between replays — call
+`sync_hyperparameters()` (done automatically by an eager `step()`) after changing them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError(f"FusedAdamW: invalid hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._plans = {}   # group index -> (key, chunk table on the device, number of chunks, hp device array, host copy of hp[:5])
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _plan(self, gi, group):
+        ps = [p for p in group["params"] if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in ps)
+        plan = self._plans.get(gi)
+        if plan is not None and plan["key"] == key:
+            return plan
+        if not ps:
+            return None
+        for p in ps:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.is_contiguous()):
+                raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients (there is no fallback path)")
+        dev = ps[0].device
+        chunk = L.load().vmae_adamw_chunk()
+        table = []
+        for p in ps:
+            st = self.state[p]
+            if not st:
+                st["step"] = torch.zeros((), dtype=torch.float32, device=dev)   # kept for state_dict compatibility
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            n = p.numel()
+            for off in range(0, n, chunk):
+                c = min(chunk, n - off)
+                table += [p.data_ptr() + 4 * off, p.grad.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off,
+                          st["exp_avg_sq"].data_ptr() + 4 * off, c]
+        old_step = float(plan["hp"][5]) if plan is not None else float(self.state[ps[0]]["step"])
+        hp = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.0, old_step], dtype=torch.float32, device=dev)
+        plan = {"key": key, "table": torch.tensor(table, dtype=torch.int64).to(dev), "chunks": len(table) // 5, "hp": hp, "host": None,
+                "params": ps}
+        self._plans[gi] = plan
+        return plan
+
+    def sync_hyperparameters(self):
+        """Push lr / betas / eps / weight decay of every group to its device array (one tiny async copy, only when they changed)."""
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plans.get(gi)
+            if plan is None:
+                continue
+            host = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]))
+            if plan["host"] != host:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("FusedAdamW: hyper-parameters changed inside a CUDA-graph capture; call sync_hyperparameters() before it")
+                plan["hp"][:5].copy_(torch.tensor(host, dtype=torch.float32), non_blocking=False)
+                plan["host"] = host
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plans.get(gi) if capturing else self._plan(gi, group)
+            if plan is None:
+                if capturing:
+                    raise RuntimeError("FusedAdamW: run one eager step() before capturing (the chunk table and the state are built there)")
+                continue
+            self.sync_hyperparameters()
+            L.check(lib.vmae_adamw_multi(ops._p(plan["table"]), plan["chunks"], ops._p(plan["hp"]), ops._stream()), "vmae_adamw_multi")
+            ops._count(2)
+        return loss
+
+    def state_dict(self):
+        # the per-parameter "step" entries mirror the group counter (torch.optim.AdamW layout)
+        for plan in self._plans.values():
+            for p in plan["params"]:
+                self.state[p]["step"].copy_(plan["hp"][5])
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plans = {}   # rebuilt (with the loaded step count) by the next step()

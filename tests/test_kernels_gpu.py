@@ -516,3 +516,53 @@ def test_attn_bwd_c_abi_accepts_workspace_for_any_head_dim(env):
         acc = torch.empty(B * Lq, H * hd, device=dev)
         L.check(lib.vmae_attn_bwd(p(qkv), p(out), p(dout), p(lse), p(delta), p(acc), p(dqkv), B, Lq, H, hd, 1.0 / math.sqrt(hd), 0.0, 0, st), "bwd")
         assert relerr(dqkv, ref) < 1e-2
+
+
+def test_fused_adamw_matches_torch_adamw(env):
+    """optim.FusedAdamW (one launch per group, device-side hyper-parameters) vs torch.optim.AdamW: same trajectory over several
+    steps incl. a learning-rate change, odd sizes, parameters that are misaligned views, two groups, and a state_dict round trip."""
+    from ssl_vit_video_analytics_b200.optim import FusedAdamW
+
+    ops, L, dev, g = env
+    shapes = [(384, 384), (1536,), (3, 5, 7), (1,), (40000,), (33, 17)]
+    base = torch.randn(sum(int(torch.tensor(s).prod()) for s in shapes) + 3, device=dev, generator=g)
+
+    def make():
+        ps, off = [], 1   # even entries: own (aligned) allocation; odd entries: views at an odd float offset (scalar path)
+        for i, s in enumerate(shapes):
+            n = int(torch.tensor(s).prod())
+            t = base[off:off + n].clone().view(s) if i % 2 == 0 else base.clone()[off:off + n].view(s)
+            off += n
+            ps.append(torch.nn.Parameter(t))
+        return ps
+
+    pa, pb = make(), make()
+    kw = dict(lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    oa = torch.optim.AdamW([{"params": pa[:3]}, {"params": pa[3:], "weight_decay": 0.0}], **kw)
+    ob = FusedAdamW([{"params": pb[:3]}, {"params": pb[3:], "weight_decay": 0.0}], **kw)
+    for it in range(6):
+        if it == 3:
+            for o in (oa, ob):
+                o.param_groups[0]["lr"] = 1e-3
+        if it == 4:   # checkpoint round trip in the middle of training
+            sd = ob.state_dict()
+            ob = FusedAdamW([{"params": pb[:3]}, {"params": pb[3:], "weight_decay": 0.0}], **kw)
+            ob.load_state_dict(sd)
+            assert ob.param_groups[0]["lr"] == 1e-3
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device=dev, generator=g) * (0.1 + it)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        oa.step()
+        ob.step()
+    for a, b in zip(pa, pb):
+        assert relerr(b.detach(), a.detach()) < 2e-6, a.shape
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    for k in sa:
+        assert float(sb[k]["step"]) == float(sa[k]["step"]) == 6.0
+        assert relerr(sb[k]["exp_avg"], sa[k]["exp_avg"]) < 2e-6
+        assert relerr(sb[k]["exp_avg_sq"], sa[k]["exp_avg_sq"]) < 2e-6
+    with pytest.raises(RuntimeError, match="fp32 CUDA"):
+        p = torch.nn.Parameter(torch.zeros(4))
+        p.grad = torch.zeros(4)
+        FusedAdamW([p]).step()
