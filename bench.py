@@ -282,11 +282,17 @@ def run_ours(args, cfg):
         bufs[0].copy_(clip_d)
         bufs[1].copy_(clip_d)
         ddp.defer_comm = world > 1
-        for t in (clip_d, bufs[0], bufs[1]):
-            graphed.capture(t)
-        if opt_graph is not None:
-            with torch.cuda.graph(opt_graph, pool=graphed.pool()):
-                opt.step()
+        try:
+            for t in (clip_d, bufs[0], bufs[1]):
+                graphed.capture(t)
+            if opt_graph is not None:
+                with torch.cuda.graph(opt_graph, pool=graphed.pool()):
+                    opt.step()
+        except Exception as exc:   # a failed capture leaves no graph behind: measure the eager step instead, and say so
+            print(f"bench.py: CUDA-graph capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
+            use_graph = False
+            ddp.defer_comm = False
+            torch.cuda.synchronize()
         for _ in range(args.warmup):
             loss = step(clip_d)
         barrier()
