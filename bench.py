@@ -220,7 +220,10 @@ def run_ours(args, cfg):
 
         def loss_fn(clip):
             return model.training_loss(clip, mask_d, vis_d)
-    opt = FusedAdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05)   # row a18: one launch, device-side hyper-parameters
+    if args.optimizer == "fused":
+        opt = FusedAdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05)   # row a18: one launch, device-side hyper-parameters
+    else:   # A/B: PyTorch's multi-tensor AdamW
+        opt = torch.optim.AdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05, fused=True, capturable=use_graph)
     clip_pinned = [clip_h.pin_memory(), clip_h.clone().pin_memory()]
     clip_d = clip_h.to(dev)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -464,7 +467,7 @@ def run_ours(args, cfg):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": "optim.FusedAdamW (vmae_adamw_multi)",
+                   "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": ("optim.FusedAdamW (vmae_adamw_multi)" if args.optimizer == "fused" else "torch.optim.AdamW(fused)"),
                    "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else ("after backward, between two graphs" if use_graph else "bucketed, overlapped with backward")), "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
@@ -493,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused = optim.FusedAdamW (default); torch = torch.optim.AdamW(fused=True), for A/B runs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step from CUDA graphs (default on; under torchrun the NCCL allreduce runs between two graphs)")
     ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit"],
