@@ -95,3 +95,24 @@ def test_gradient_clipping_bounds_the_update():
     E.train_one_epoch(1, model, _loader(1), opt, None, None, torch.device("cpu"), cfg, Log())
     w1 = torch.cat([p.detach().flatten() for p in model.parameters()])
     assert float((w1 - w0).norm()) <= 1e-3 * 1.0001           # SGD with lr 1: the step is the clipped gradient
+
+
+def test_fused_adamw_host_side_contract():
+    """optim.FusedAdamW: torch.optim.AdamW's constructor contract (defaults, param groups, validation); no CPU update path."""
+    import pytest
+    import torch
+
+    from ssl_vit_video_analytics_b200.optim import FusedAdamW
+
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdamW([{"params": [p], "weight_decay": 0.0}], lr=5e-4, weight_decay=0.05)
+    ref = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(4))], lr=5e-4, weight_decay=0.05)
+    assert opt.defaults["betas"] == ref.defaults["betas"] and opt.defaults["eps"] == ref.defaults["eps"]
+    assert opt.param_groups[0]["weight_decay"] == 0.0 and opt.param_groups[0]["lr"] == 5e-4
+    for bad in (dict(lr=-1.0), dict(betas=(1.0, 0.9)), dict(eps=-1e-8), dict(weight_decay=-0.1)):
+        with pytest.raises(ValueError):
+            FusedAdamW([p], **bad)
+    opt.step()                      # no gradient yet: nothing to do, nothing to launch
+    p.grad = torch.zeros(4)
+    with pytest.raises(RuntimeError, match="fp32 CUDA"):
+        opt.step()                  # a CPU parameter fails loudly (no fallback)
