@@ -388,34 +388,33 @@ __global__ void __launch_bounds__(MO_THREADS) decoder_input_fwd_kernel(const __n
   }
 }
 
-// K5 backward. Masked rows reduce into dmask_token (register partials -> smem -> one red.add per column per CTA);
-// visible rows produce dz (bf16) and scatter-add into dtpos / dspos.
+// K5 backward. One CTA per (clip, temporal position): its L rows share one temporal-position row, so the dtpos contribution is
+// summed in registers and shared memory and leaves the CTA as ONE red.add per column (row-wise atomics on the Tp rows of dtpos
+// serialised ~1 250 same-address updates per element: 95 us for a 24-us read). Masked rows reduce into dmask_token the same
+// way; visible rows produce dz (bf16) and scatter-add into dspos (L distinct rows: no contention worth removing).
 __global__ void __launch_bounds__(MO_THREADS) decoder_input_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ vis_idx,
                                                                        const unsigned char* __restrict__ mask, __nv_bfloat16* __restrict__ dz,
                                                                        float* __restrict__ dtpos, float* __restrict__ dspos,
                                                                        float* __restrict__ dmask_token, int B, int Tp, int L, int n_vis, int D) {
   extern __shared__ float mt_smem[];  // [MO_WARPS][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long rows = (long long)B * Tp * L;
-  const long long wstride = (long long)gridDim.x * MO_WARPS;
+  const int seg = blockIdx.x, b = seg / Tp, tp = seg % Tp;
   constexpr int MAXV = 8;  // D <= 1024
-  float4 acc[MAXV];
+  float4 acc[MAXV], acc_tp[MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = (long long)blockIdx.x * MO_WARPS + warp; row < rows; row += wstride) {
-    const int l = (int)(row % L);
-    const int tp = (int)((row / L) % Tp);
-    const int b = (int)(row / ((long long)L * Tp));
+  for (int i = 0; i < MAXV; ++i) acc[i] = acc_tp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = warp; l < L; l += MO_WARPS) {
+    const long long row = (long long)seg * L + l;
     const float* src = dx + row * D;
+    float4 v[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      v[i] = (d < D) ? __ldg(reinterpret_cast<const float4*>(src + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (mask[row]) {
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int d = (i * 32 + lane) * 4;
-        if (d < D) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-        }
-      }
+      for (int i = 0; i < MAXV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
       if (!vis_idx && dz) {  // blend form: dz covers every token; masked rows get zero gradient
         for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<uint2*>(dz + row * D + d) = make_uint2(0u, 0u);
       }
@@ -427,59 +426,80 @@ __global__ void __launch_bounds__(MO_THREADS) decoder_input_bwd_kernel(const flo
       if (slot < 0) continue;
       zrow = ((long long)b * Tp + tp) * n_vis + slot;
     }
-    for (int d = lane * 4; d < D; d += 128) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d >= D) continue;
       if (dz) {
-        __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(v[i].x, v[i].y), a1 = __floats2bfloat162_rn(v[i].z, v[i].w);
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&a0);
         u.y = *reinterpret_cast<uint32_t*>(&a1);
         *reinterpret_cast<uint2*>(dz + zrow * D + d) = u;
       }
-      if (dtpos) {
-        float* p = dtpos + (long long)tp * D + d;
-        atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
-      }
+      acc_tp[i].x += v[i].x; acc_tp[i].y += v[i].y; acc_tp[i].z += v[i].z; acc_tp[i].w += v[i].w;
       if (dspos) {
         float* p = dspos + (long long)l * D + d;
-        atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+        atomicAdd(p, v[i].x); atomicAdd(p + 1, v[i].y); atomicAdd(p + 2, v[i].z); atomicAdd(p + 3, v[i].w);
       }
     }
   }
-  if (!dmask_token) return;
+  float* mine = mt_smem + (size_t)warp * D;
+  auto block_sum_to = [&](const float4 (&a)[MAXV], float* dst) {   // dst[d] += sum over the CTA's warps of a
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d < D) *reinterpret_cast<float4*>(mine + d) = a[i];
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += MO_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < MO_WARPS; ++w) t += mt_smem[(size_t)w * D + d];
+      atomicAdd(dst + d, t);
+    }
+    __syncthreads();
+  };
+  if (dmask_token) block_sum_to(acc, dmask_token);
+  if (dtpos) block_sum_to(acc_tp, dtpos + (long long)tp * D);
+}
+
+// Encoder-side positional rows (tubelet gather backward): one CTA per (clip, temporal position), as above.
+__global__ void __launch_bounds__(MO_THREADS) pos_rows_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ vis_idx,
+                                                                  float* __restrict__ dtpos, float* __restrict__ dspos, int B, int Tp, int n_vis,
+                                                                  int D) {
+  extern __shared__ float mt_smem[];  // [MO_WARPS][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x, b = seg / Tp, tp = seg % Tp;
+  constexpr int MAXV = 8;  // D <= 1024
+  float4 acc_tp[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) acc_tp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = warp; i0 < n_vis; i0 += MO_WARPS) {
+    const long long row = (long long)seg * n_vis + i0;
+    const int l = vis_idx[(long long)b * n_vis + i0];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d >= D) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dx + row * D + d));
+      acc_tp[i].x += v.x; acc_tp[i].y += v.y; acc_tp[i].z += v.z; acc_tp[i].w += v.w;
+      float* q = dspos + (long long)l * D + d;
+      atomicAdd(q, v.x); atomicAdd(q + 1, v.y); atomicAdd(q + 2, v.z); atomicAdd(q + 3, v.w);
+    }
+  }
   float* mine = mt_smem + (size_t)warp * D;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int d = (i * 32 + lane) * 4;
-    if (d < D) *reinterpret_cast<float4*>(mine + d) = acc[i];
+    if (d < D) *reinterpret_cast<float4*>(mine + d) = acc_tp[i];
   }
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += MO_THREADS) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < MO_WARPS; ++w) t += mt_smem[(size_t)w * D + d];
-    atomicAdd(dmask_token + d, t);
-  }
-}
-
-__global__ void __launch_bounds__(MO_THREADS) pos_rows_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ vis_idx,
-                                                                  float* __restrict__ dtpos, float* __restrict__ dspos, int B, int Tp, int n_vis,
-                                                                  int D) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long rows = (long long)B * Tp * n_vis;
-  const long long wstride = (long long)gridDim.x * MO_WARPS;
-  for (long long row = (long long)blockIdx.x * MO_WARPS + warp; row < rows; row += wstride) {
-    const int i = (int)(row % n_vis);
-    const int tp = (int)((row / n_vis) % Tp);
-    const int b = (int)(row / ((long long)n_vis * Tp));
-    const int l = vis_idx[(long long)b * n_vis + i];
-    for (int d = lane * 4; d < D; d += 128) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(dx + row * D + d));
-      float* p = dtpos + (long long)tp * D + d;
-      atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
-      float* q = dspos + (long long)l * D + d;
-      atomicAdd(q, v.x); atomicAdd(q + 1, v.y); atomicAdd(q + 2, v.z); atomicAdd(q + 3, v.w);
-    }
+    atomicAdd(dtpos + (long long)tp * D + d, t);
   }
 }
 
@@ -704,20 +724,18 @@ extern "C" int vmae_decoder_input_bwd(const float* dx_dec, const int* vis_idx, c
                                       float* dmask_token, int B, int Tp, int L, int n_vis, int D, void* stream) {
   VMAE_CHECK_ARG(dx_dec && mask, "vmae_decoder_input_bwd: null pointer");
   VMAE_CHECK_ARG(B > 0 && Tp > 0 && L > 0 && D > 0 && D % 4 == 0 && D <= 1024, "vmae_decoder_input_bwd: bad shape (D <= 1024, D %% 4 == 0)");
-  const long long rows = (long long)B * Tp * L;
-  long long g = (rows + MO_WARPS - 1) / MO_WARPS;
-  const long long cap = (long long)num_sms() * 4;
   const size_t smem = (size_t)MO_WARPS * D * sizeof(float);
-  decoder_input_bwd_kernel<<<(int)(g > cap ? cap : g), MO_THREADS, smem, (cudaStream_t)stream>>>(dx_dec, vis_idx, mask, (__nv_bfloat16*)dz, dtpos, dspos,
-                                                                                                   dmask_token, B, Tp, L, n_vis, D);
+  decoder_input_bwd_kernel<<<B * Tp, MO_THREADS, smem, (cudaStream_t)stream>>>(dx_dec, vis_idx, mask, (__nv_bfloat16*)dz, dtpos, dspos,
+                                                                                 dmask_token, B, Tp, L, n_vis, D);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
 
 extern "C" int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* dspos, int B, int Tp, int n_vis, int D, void* stream) {
-  VMAE_CHECK_ARG(dx && vis_idx && dtpos && dspos && B > 0 && Tp > 0 && n_vis > 0 && D % 4 == 0, "vmae_pos_rows_bwd: bad args");
-  const long long rows = (long long)B * Tp * n_vis;
-  pos_rows_bwd_kernel<<<mo_grid(rows), MO_THREADS, 0, (cudaStream_t)stream>>>(dx, vis_idx, dtpos, dspos, B, Tp, n_vis, D);
+  VMAE_CHECK_ARG(dx && vis_idx && dtpos && dspos && B > 0 && Tp > 0 && n_vis > 0 && D % 4 == 0 && D <= 1024,
+                 "vmae_pos_rows_bwd: bad args (D <= 1024, D %% 4 == 0)");
+  const size_t smem = (size_t)MO_WARPS * D * sizeof(float);
+  pos_rows_bwd_kernel<<<B * Tp, MO_THREADS, smem, (cudaStream_t)stream>>>(dx, vis_idx, dtpos, dspos, B, Tp, n_vis, D);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
