@@ -516,8 +516,15 @@ def attention(qkv, num_heads):
     return AttentionFn.apply(qkv, num_heads)
 
 
-# (TensorImpl id, fp32 stream gradient, its bf16 copy) handed from one block's backward to the next one's
+# ((data pointer, numel), fp32 stream gradient, its bf16 copy) handed from one block's backward to the next one's. Matching is
+# by storage, not by tensor identity: between two decoder layers the gradient passes through view/reshape backward nodes, which
+# wrap the same memory in a new tensor. The entry holds a strong reference, so the memory cannot be recycled while it lives and
+# autograd cannot accumulate into it in place (its use count is > 1).
 _GRAD_SHADOW = [None]
+
+
+def _shadow_key(t):
+    return (t.data_ptr(), t.numel())
 
 # When a parameter already owns a contiguous fp32 .grad (e.g. a view into a GradientBucketer bucket), the fused block
 # accumulates into it directly (TMA reduce-add / red.add) and returns None to autograd: no zero-filled temporary, no
@@ -597,7 +604,8 @@ class TransformerBlockFn(torch.autograd.Function):
         if p_drop > 0.0:
             dx2_b = dropout_apply(dx2, p_drop, s_d2, out_dtype=BF16)      # gradient entering fc2 = dropout2 mask * dx2 / (1-p)
         else:
-            dx2_b = sh[2] if (sh is not None and sh[0] == dx2._cdata) else cast_bf16(dx2)
+            hit = sh is not None and dx2.dtype == F32 and sh[0] == _shadow_key(dx2)
+            dx2_b = sh[2].view(dx2.shape) if hit else cast_bf16(dx2)
         _GRAD_SHADOW[0] = None
         P = ctx.params  # ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b
         tgt = [(_direct_grad(p) if ctx.needs_input_grad[i + 1] else None) for i, p in enumerate(P)]
@@ -617,7 +625,7 @@ class TransformerBlockFn(torch.autograd.Function):
         dln1 = linear_dgrad(dqkv, wq)
         dwq, dbq = linear_wgrad_bias(dqkv, ln1, t_wq, t_bq)
         dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, dgamma=t_g1, dbeta=t_b1, want_bf16=True)
-        _GRAD_SHADOW[0] = (dx._cdata, dx, dx_b)  # strong refs: the TensorImpl cannot be recycled while the entry lives
+        _GRAD_SHADOW[0] = (_shadow_key(dx), dx, dx_b)
         grads = [dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2]
         out = []
         # reverse order ~ the order in which the gradients became final (fc2 first), so buckets close as early as possible
