@@ -21,39 +21,69 @@ class FusedAdamW(torch.optim.Optimizer):
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError(f"FusedAdamW: invalid hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._plans = {}   # group index -> (key, chunk table on the device, number of chunks, hp device array, host copy of hp[:5])
+        self._plans = {}   # group index -> plan (chunk table on the device, its host/pinned images, hp device array, ...)
 
     # ------------------------------------------------------------------------------------------------------------
     def _plan(self, gi, group):
+        """Chunk table of a group. The parameter / state columns are built once; the gradient column is refreshed (one small
+        async copy from pinned memory, no synchronisation) whenever the gradients moved, e.g. after `zero_grad(set_to_none=True)`."""
         ps = [p for p in group["params"] if p.grad is not None]
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in ps)
-        plan = self._plans.get(gi)
-        if plan is not None and plan["key"] == key:
-            return plan
         if not ps:
             return None
+        pkey = tuple((p.data_ptr(), p.numel()) for p in ps)
+        gkey = tuple(p.grad.data_ptr() for p in ps)
+        plan = self._plans.get(gi)
+        if plan is not None and plan["pkey"] == pkey and plan["gkey"] == gkey:
+            return plan
         for p in ps:
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.is_contiguous()):
                 raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients (there is no fallback path)")
         dev = ps[0].device
-        chunk = L.load().vmae_adamw_chunk()
-        table = []
-        for p in ps:
-            st = self.state[p]
-            if not st:
-                st["step"] = torch.zeros((), dtype=torch.float32, device=dev)   # kept for state_dict compatibility
-                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            n = p.numel()
-            for off in range(0, n, chunk):
-                c = min(chunk, n - off)
-                table += [p.data_ptr() + 4 * off, p.grad.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off,
-                          st["exp_avg_sq"].data_ptr() + 4 * off, c]
-        old_step = float(plan["hp"][5]) if plan is not None else float(self.state[ps[0]]["step"])
-        hp = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.0, old_step], dtype=torch.float32, device=dev)
-        plan = {"key": key, "table": torch.tensor(table, dtype=torch.int64).to(dev), "chunks": len(table) // 5, "hp": hp, "host": None,
-                "params": ps}
-        self._plans[gi] = plan
+        if plan is None or plan["pkey"] != pkey:
+            chunk = L.load().vmae_adamw_chunk()
+            idx, off, cnt, cols = [], [], [], [[], [], []]
+            for k, p in enumerate(ps):
+                st = self.state[p]
+                if not st:
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=dev)   # kept for state_dict compatibility
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                n = p.numel()
+                for o in range(0, n, chunk):
+                    idx.append(k)
+                    off.append(4 * o)
+                    cnt.append(min(chunk, n - o))
+                    cols[0].append(p.data_ptr() + 4 * o)
+                    cols[1].append(st["exp_avg"].data_ptr() + 4 * o)
+                    cols[2].append(st["exp_avg_sq"].data_ptr() + 4 * o)
+            # the step count survives a rebuild: from the previous plan (device-to-device), else from a loaded state_dict
+            hp = torch.zeros(6, dtype=torch.float32, device=dev)
+            if plan is not None:
+                hp[5:6].copy_(plan["hp"][5:6])
+            else:
+                hp[5:6].copy_(self.state[ps[0]]["step"].reshape(1).to(torch.float32))
+            host = torch.zeros((len(idx), 5), dtype=torch.int64)
+            host[:, 0] = torch.tensor(cols[0], dtype=torch.int64)
+            host[:, 2] = torch.tensor(cols[1], dtype=torch.int64)
+            host[:, 3] = torch.tensor(cols[2], dtype=torch.int64)
+            host[:, 4] = torch.tensor(cnt, dtype=torch.int64)
+            plan = {"pkey": pkey, "gkey": None, "idx": torch.tensor(idx, dtype=torch.int64), "off": torch.tensor(off, dtype=torch.int64),
+                    "host": host, "staging": [host.clone().pin_memory() for _ in range(2)], "staged": [None, None], "turn": 0,
+                    "table": torch.empty((len(idx), 5), dtype=torch.int64, device=dev), "chunks": len(idx), "hp": hp, "hyper": None, "params": ps}
+            self._plans[gi] = plan
+        # gradient column -> pinned staging buffer (two of them, each guarded by the event of its last copy) -> device table
+        t = plan["turn"]
+        plan["turn"] = 1 - t
+        if plan["staged"][t] is not None:
+            plan["staged"][t].synchronize()
+        stage = plan["staging"][t]
+        stage.copy_(plan["host"])
+        stage[:, 1] = torch.tensor(gkey, dtype=torch.int64)[plan["idx"]] + plan["off"]
+        plan["table"].copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        plan["staged"][t] = ev
+        plan["gkey"] = gkey
         return plan
 
     def sync_hyperparameters(self):
@@ -63,11 +93,11 @@ class FusedAdamW(torch.optim.Optimizer):
             if plan is None:
                 continue
             host = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]))
-            if plan["host"] != host:
+            if plan["hyper"] != host:
                 if torch.cuda.is_current_stream_capturing():
                     raise RuntimeError("FusedAdamW: hyper-parameters changed inside a CUDA-graph capture; call sync_hyperparameters() before it")
                 plan["hp"][:5].copy_(torch.tensor(host, dtype=torch.float32), non_blocking=False)
-                plan["host"] = host
+                plan["hyper"] = host
 
     @torch.no_grad()
     def step(self, closure=None):
