@@ -116,3 +116,18 @@ def test_fused_adamw_host_side_contract():
     p.grad = torch.zeros(4)
     with pytest.raises(RuntimeError, match="fp32 CUDA"):
         opt.step()                  # a CPU parameter fails loudly (no fallback)
+
+
+def test_graphed_train_step_host_side_errors():
+    """graph_step.GraphedTrainStep refuses what cannot work, without a GPU: a CPU buffer, a buffer that was never captured."""
+    import pytest
+    import torch
+
+    from ssl_vit_video_analytics_b200.graph_step import GraphedTrainStep
+
+    gs = GraphedTrainStep(lambda clip: clip.sum())
+    with pytest.raises(RuntimeError, match="CUDA input buffer"):
+        gs.capture(torch.zeros(2))
+    with pytest.raises(RuntimeError, match="not captured"):
+        gs.replay(torch.zeros(2))
+    assert gs.pool() is None
