@@ -25,6 +25,11 @@ dout = torch.randn(B * Lq, H * hd, device=dev, generator=g).bfloat16()
 clip = torch.randn(16, 3, 16, 224, 224, device=dev, generator=g)
 pred = torch.randn(16, 1568, 1536, device=dev, generator=g).bfloat16()
 mask = (torch.rand(16, 1568, device=dev, generator=g) < 0.9)
+from ssl_vit_video_analytics_b200.optim import FusedAdamW  # noqa: E402
+wparams = [torch.nn.Parameter(torch.randn(1536, 384, device=dev, generator=g)) for _ in range(36)]   # 21 M parameters
+for p_ in wparams:
+    p_.grad = torch.randn_like(p_) * 0.01
+adamw = FusedAdamW(wparams, lr=1e-4, weight_decay=0.05)
 for _ in range(2):
     ops.gemm(x, w1, M, 1536, D, bias=b1)                                            # 1 qkv/pred-like: bias, bf16 out
     act = ops.gemm(x, w1, M, 1536, D, bias=b1, act=L.ACT_GELU, aux_out=pre)        # 2 fc1: bias + GELU + pre-activation
@@ -38,5 +43,6 @@ for _ in range(2):
     ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd)                                # delta, single-pass backward, dQ convert
     ops.attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, fused=False)                   # delta, dQ, dK/dV (two-kernel form)
     ops.masked_mse(pred, clip, mask, 2, 16, 1)                                     # 13-14 loss (+ finalize)
+    adamw.step()                                                                   # AdamW over 36 tensors in one launch (+ tick)
 torch.cuda.synchronize()
 print("done")
