@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VMAE_ABI_VERSION 2
+#define VMAE_ABI_VERSION 3
 
 #define VMAE_ERR_BAD_ARG (-1)
 #define VMAE_ERR_UNSUPPORTED (-2)
@@ -210,6 +210,37 @@ int vmae_add_gaussian_noise(const void* z, void* out, int dtype, float* eps_out,
                             unsigned long long seed, unsigned long long offset, void* stream);
 /* K9 helper (FedAvg pre-scale, federated/fed_loop.py:45-49): y = alpha * x (+ y if accumulate), fp32 */
 int vmae_scale_f32(const float* x, float* y, float alpha, int accumulate, long long n, void* stream);
+
+/* ---- stack 2: latent-space MAE mask / gather logic (tinyvit_mae.py:104-114) -------------------------------------------
+ * vmae_mask_row_indices: mask uint8 [B, N] -> idx int32 [B * n_sel]: ascending GLOBAL row numbers b*N + n of the entries with
+ *   (mask != 0) == want, n_sel per clip; this is the row order of torch's boolean gather `rec[token_mask]` (:113-114) when every
+ *   clip holds n_sel hits (both modes of make_token_mask do). flag (optional device int, zeroed by the caller): bit 0 = some clip
+ *   had fewer hits (padded with -1), bit 1 = some clip had more. No host sync.
+ * vmae_mask_token_blend_fwd: out[r,:] = mask[r] ? mask_token[:] : tok[r,:]   (torch.where, :107-108); tok/out bf16 or fp32.
+ * vmae_mask_token_blend_bwd: dtok[r,:] = mask[r] ? 0 : dout[r,:] (dtok may be NULL); dmask_token[:] += sum of masked rows (may be NULL).
+ * vmae_gather_rows: out[i,:] = src[idx[i],:] (idx < 0 -> zero row).  vmae_scatter_rows: dst = 0; dst[idx[i],:] = src[i,:]
+ *   (the backward of the gather; idx unique). */
+int vmae_mask_row_indices(const unsigned char* mask, int* idx, int* flag, int B, int N, int n_sel, int want, void* stream);
+int vmae_mask_token_blend_fwd(const void* tok, int dtype, const unsigned char* mask, const float* mask_token, void* out,
+                              long long rows, int D, void* stream);
+int vmae_mask_token_blend_bwd(const void* dout, int dtype, const unsigned char* mask, void* dtok, float* dmask_token,
+                              long long rows, int D, void* stream);
+int vmae_gather_rows(const void* src, int dtype, const int* idx, void* out, long long n_out, int D, void* stream);
+int vmae_scatter_rows(const void* src, int dtype, const int* idx, void* dst, long long n_src, long long n_dst_rows, int D,
+                      void* stream);
+
+/* F.adaptive_avg_pool2d(f, (s, s)) of tinyvit_backbone.py:74-81 on a channels-last bf16 map x [N,H,W,C] -> out fp32 [N, s*s, C];
+ * bin i covers [floor(i*H/s), ceil((i+1)*H/s)). bwd: dx bf16 [N,H,W,C] from dout fp32 [N, s*s, C]. */
+int vmae_adaptive_avgpool_fwd(const void* x, float* out, int N, int H, int W, int C, int s, void* stream);
+int vmae_adaptive_avgpool_bwd(const float* dout, void* dx, int N, int H, int W, int C, int s, void* stream);
+
+/* ---- K10: fused softmax cross-entropy of the finetune head (train_finetune.py:86-107, nn.CrossEntropyLoss, mean reduction) ----
+ * fwd: logits bf16|fp32 [rows, C], labels int64 [rows] -> lse fp32 [rows] (saved), row_loss fp32 [rows], loss fp32 scalar = mean.
+ * bwd: dlogits (dtype of logits) = (softmax(logits) - onehot(label)) * gout[0] / rows. */
+int vmae_softmax_ce_fwd(const void* logits, int dtype, const long long* labels, float* lse, float* row_loss, float* loss,
+                        long long rows, int C, void* stream);
+int vmae_softmax_ce_bwd(const void* logits, int dtype, const long long* labels, const float* lse, const float* gout,
+                        void* dlogits, long long rows, int C, void* stream);
 
 #ifdef __cplusplus
 }

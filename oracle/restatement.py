@@ -90,6 +90,29 @@ def mae_l2_loss(pred: Tensor, target: Tensor, normalize: bool = True) -> Tensor:
     return ((pred - target) ** 2).mean()
 
 
+def mae_l1_loss(pred: Tensor, target: Tensor) -> Tensor:
+    """mae/losses.py:44-49."""
+    return (pred - target).abs().mean()
+
+
+def mae_cosine_loss(pred: Tensor, target: Tensor, eps: float = 1e-6) -> Tensor:
+    """mae/losses.py:52-63."""
+    p = F.normalize(pred, dim=-1, eps=eps)
+    t = F.normalize(target, dim=-1, eps=eps)
+    return 1.0 - (p * t).sum(dim=-1).mean()
+
+
+def mae_recon_loss(pred: Tensor, target: Tensor, loss_type: str = "l2", normalize_target: bool = True) -> Tensor:
+    """mae/losses.py:69-90 (keyword form used by mae/engine.py:87)."""
+    if loss_type == "l2":
+        return mae_l2_loss(pred, target, normalize_target)
+    if loss_type == "l1":
+        return mae_l1_loss(pred, target)
+    if loss_type == "cosine":
+        return mae_cosine_loss(pred, target)
+    raise ValueError(f"Unknown MAE loss type: {loss_type}")
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # TinyViT encoder (models/tiny_vit.py)
 # ----------------------------------------------------------------------------------------------------------------------
@@ -102,7 +125,15 @@ def _conv_bn(sd: SD, p: str, x: Tensor, stride: int, pad: int, groups: int, bn_t
                         False, 0.0, 1e-5)
 
 
-def _mbconv(sd: SD, p: str, x: Tensor, stride: int, bn_train: bool) -> Tensor:
+def _drop_path(y: Tensor, drop) -> Tensor:
+    """timm DropPath (tiny_vit.py:5) with the per-sample keep mask supplied: y * keep[b] / keep_prob. drop = (keep_prob, keep[B])."""
+    if drop is None:
+        return y
+    keep_prob, keep = drop
+    return y * (keep.to(y.dtype).reshape((y.shape[0],) + (1,) * (y.ndim - 1)) / keep_prob)
+
+
+def _mbconv(sd: SD, p: str, x: Tensor, stride: int, bn_train: bool, drop=None) -> Tensor:
     """tiny_vit.py:36-56 (+ SELayer :20-34); expand_ratio 4; residual iff stride 1 and in == out."""
     cin = x.shape[1]
     h = F.gelu(_conv_bn(sd, p + ".conv.0", x, 1, 0, 1, bn_train))
@@ -112,7 +143,7 @@ def _mbconv(sd: SD, p: str, x: Tensor, stride: int, bn_train: bool) -> Tensor:
     g = torch.sigmoid(F.linear(F.relu(F.linear(g, sd[p + ".conv.4.fc.0.weight"])), sd[p + ".conv.4.fc.2.weight"]))
     h = h * g[:, :, None, None]
     h = _conv_bn(sd, p + ".conv.5", h, 1, 0, 1, bn_train)
-    return x + h if (stride == 1 and cin == h.shape[1]) else h
+    return x + _drop_path(h, drop) if (stride == 1 and cin == h.shape[1]) else h
 
 
 def attention_core(qkv: Tensor, num_heads: int) -> Tensor:
@@ -125,23 +156,26 @@ def attention_core(qkv: Tensor, num_heads: int) -> Tensor:
 
 
 def transformer_block(x: Tensor, ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b,
-                      num_heads: int) -> Tensor:
-    """Pre-LN block: tiny_vit.py:122-126 and nn.TransformerEncoderLayer(norm_first=True, gelu) with dropout inactive."""
+                      num_heads: int, drop=None) -> Tensor:
+    """Pre-LN block: tiny_vit.py:122-126 and nn.TransformerEncoderLayer(norm_first=True, gelu) with dropout inactive.
+    drop = (keep_prob, keep_attn[B], keep_mlp[B]): the block's DropPath (:124-125), two draws of the same module, masks supplied."""
     D = x.shape[-1]
+    d1 = None if drop is None else (drop[0], drop[1])
+    d2 = None if drop is None else (drop[0], drop[2])
     h = F.layer_norm(x, (D,), ln1_w, ln1_b, 1e-5)
-    x = x + F.linear(attention_core(F.linear(h, qkv_w, qkv_b), num_heads), proj_w, proj_b)
+    x = x + _drop_path(F.linear(attention_core(F.linear(h, qkv_w, qkv_b), num_heads), proj_w, proj_b), d1)
     h = F.layer_norm(x, (D,), ln2_w, ln2_b, 1e-5)
-    return x + F.linear(F.gelu(F.linear(h, fc1_w, fc1_b)), fc2_w, fc2_b)
+    return x + _drop_path(F.linear(F.gelu(F.linear(h, fc1_w, fc1_b)), fc2_w, fc2_b), d2)
 
 
-def _tinyvit_block(sd: SD, p: str, x: Tensor, num_heads: int) -> Tensor:
+def _tinyvit_block(sd: SD, p: str, x: Tensor, num_heads: int, drop=None) -> Tensor:
     """tiny_vit.py:108-130 on an NCHW map."""
     B, C, H, W = x.shape
     t = x.flatten(2).transpose(1, 2)
     t = transformer_block(t, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], sd[p + ".attn.qkv.weight"], sd[p + ".attn.qkv.bias"],
                           sd[p + ".attn.proj.weight"], sd[p + ".attn.proj.bias"], sd[p + ".norm2.weight"], sd[p + ".norm2.bias"],
                           sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"], sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"],
-                          num_heads)
+                          num_heads, drop)
     return t.transpose(1, 2).reshape(B, C, H, W)
 
 
@@ -149,8 +183,11 @@ TINYVIT_DEPTHS = (2, 2, 6, 2)
 TINYVIT_HEADS = (3, 6, 12, 18)
 
 
-def tinyvit_forward(sd: SD, x: Tensor, prefix: str = "", num_stages: int = 3, bn_train: bool = True) -> Tensor:
-    """tiny_vit.py:166-186 (forward_stage3 = 3 stages, forward = 4) for the 21M variant (:188-191)."""
+def tinyvit_forward(sd: SD, x: Tensor, prefix: str = "", num_stages: int = 3, bn_train: bool = True, drop_masks=None) -> Tensor:
+    """tiny_vit.py:166-186 (forward_stage3 = 3 stages, forward = 4) for the 21M variant (:188-191).
+    drop_masks: {"stages.S.J": (keep_prob, keep[B])} for MBConv blocks, (keep_prob, keep_attn[B], keep_mlp[B]) for TinyViTBlocks —
+    the stochastic-depth masks of :146,158-162 supplied from outside (None = drop-path inactive)."""
+    dm = drop_masks or {}
     p = prefix + "patch_embed.patch_embed"
     x = F.gelu(_conv_bn(sd, p + ".0", x, 2, 1, 1, bn_train))
     x = _conv_bn(sd, p + ".2", x, 1, 1, 1, bn_train)
@@ -161,9 +198,9 @@ def tinyvit_forward(sd: SD, x: Tensor, prefix: str = "", num_stages: int = 3, bn
             j += 1
         for _ in range(TINYVIT_DEPTHS[s]):
             if s == 0:
-                x = _mbconv(sd, f"{prefix}stages.{s}.{j}", x, 1, bn_train)
+                x = _mbconv(sd, f"{prefix}stages.{s}.{j}", x, 1, bn_train, dm.get(f"stages.{s}.{j}"))
             else:
-                x = _tinyvit_block(sd, f"{prefix}stages.{s}.{j}", x, TINYVIT_HEADS[s])
+                x = _tinyvit_block(sd, f"{prefix}stages.{s}.{j}", x, TINYVIT_HEADS[s], dm.get(f"stages.{s}.{j}"))
             j += 1
     return x
 
@@ -184,17 +221,42 @@ def _decoder(sd: SD, x: Tensor, depth: int, heads: int) -> Tensor:
     return F.linear(x, sd["decoder_pred.weight"], sd["decoder_pred.bias"])
 
 
-def tiny_video_mae_forward(sd: SD, clip: Tensor, mask: Tensor, decoder_depth: int, decoder_heads: int, bn_train: bool = True) -> Tensor:
-    """mae_vit_adapter.py:75-117 with dropout / drop-path inactive."""
+def tiny_video_mae_forward(sd: SD, clip: Tensor, mask: Tensor, decoder_depth: int, decoder_heads: int, bn_train: bool = True,
+                           drop_masks=None) -> Tensor:
+    """mae_vit_adapter.py:75-117 with decoder dropout inactive; encoder drop-path only through supplied masks."""
     B, C, T, H, W = clip.shape
     frames = clip.permute(0, 2, 1, 3, 4).flatten(0, 1)
-    latent = tinyvit_forward(sd, frames, "encoder.", 3, bn_train).flatten(2).transpose(1, 2)
+    latent = tinyvit_forward(sd, frames, "encoder.", 3, bn_train, drop_masks).flatten(2).transpose(1, 2)
     L = latent.shape[1]
     x = F.linear(latent, sd["enc_to_dec.weight"], sd["enc_to_dec.bias"]).view(B, T, L, -1)
     x = x + (sd["temporal_pos_embed"] + sd["spatial_pos_embed"])
     m = mask.unsqueeze(-1).type_as(x)
     x = (x * (1 - m) + sd["mask_token"] * m).flatten(1, 2)
     return _decoder(sd, x, decoder_depth, decoder_heads)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# stack 2: latent-space MAE (models/tinyvit_mae.py); the timm encoder is out of scope, tokens are an input here
+# ----------------------------------------------------------------------------------------------------------------------
+def mae_decoder_forward(sd: SD, x: Tensor, depth: int, heads: int, prefix: str = "decoder.") -> Tensor:
+    """tinyvit_mae.py:12-32 — proj -> nn.TransformerEncoder(norm_first, gelu) x depth -> pred (no final norm), dropout inactive."""
+    x = F.linear(x, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
+    for i in range(depth):
+        p = f"{prefix}blocks.layers.{i}"
+        x = transformer_block(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], sd[p + ".self_attn.in_proj_weight"],
+                              sd[p + ".self_attn.in_proj_bias"], sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"],
+                              sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], sd[p + ".linear1.weight"], sd[p + ".linear1.bias"],
+                              sd[p + ".linear2.weight"], sd[p + ".linear2.bias"], heads)
+    return F.linear(x, sd[prefix + "pred.weight"], sd[prefix + "pred.bias"])
+
+
+def tinyvit_mae_forward(sd: SD, tok: Tensor, token_mask: Tensor, depth: int, heads: int):
+    """tinyvit_mae.py:104-114 from the encoder tokens tok [B, N, D] on: mask-token substitution (torch.where), decoder,
+    row-major boolean gathers -> (pred [N_mask, D], target [N_mask, D] detached)."""
+    B, N, D = tok.shape
+    tok_in = torch.where(token_mask.unsqueeze(-1), sd["mask_token"].expand(B, N, D), tok)
+    rec = mae_decoder_forward(sd, tok_in, depth, heads)
+    return rec[token_mask], tok[token_mask].detach()
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -62,6 +62,15 @@ SIGNATURES = {
     "vmae_colsum_accum": [_p, _i, _ll, _p, _ll, _i, _p],
     "vmae_add_gaussian_noise": [_p, _p, _i, _p, _ll, _f, _ull, _ull, _p],
     "vmae_scale_f32": [_p, _p, _f, _i, _ll, _p],
+    "vmae_mask_row_indices": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "vmae_mask_token_blend_fwd": [_p, _i, _p, _p, _p, _ll, _i, _p],
+    "vmae_mask_token_blend_bwd": [_p, _i, _p, _p, _p, _ll, _i, _p],
+    "vmae_gather_rows": [_p, _i, _p, _p, _ll, _i, _p],
+    "vmae_scatter_rows": [_p, _i, _p, _p, _ll, _ll, _i, _p],
+    "vmae_adaptive_avgpool_fwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_adaptive_avgpool_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_softmax_ce_fwd": [_p, _i, _p, _p, _p, _p, _ll, _i, _p],
+    "vmae_softmax_ce_bwd": [_p, _i, _p, _p, _p, _p, _ll, _i, _p],
 }
 _RESTYPES = {"vmae_last_error": C.c_char_p}
 

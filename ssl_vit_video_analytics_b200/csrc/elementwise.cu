@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(EW_THREADS) gaussian_noise_kernel(const T* __r
       if (k < n) {
         float v;
         if constexpr (sizeof(T) == 4) v = (float)z[k]; else v = __bfloat162float(z[k]);
-        v += sigma * ev[j];
+        v = __fmaf_rn(sigma, ev[j], v);   // one rounding: round(z + sigma * eps)
         if constexpr (sizeof(T) == 4) out[k] = v; else out[k] = __float2bfloat16_rn(v);
         if (eps_out) eps_out[k] = ev[j];
       }

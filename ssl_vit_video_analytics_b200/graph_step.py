@@ -8,8 +8,12 @@ Rules the caller has to follow (they are the usual ones of `torch.cuda.graph`):
   * run everything — model construction, `GradientBucketer`, the eager warm-up steps — on a NON-default stream
     (`use_side_stream()` below): autograd binds every gradient accumulator to the stream it first saw, and a capture may not
     synchronise with the legacy default stream;
-  * the optimizer must be built with `capturable=True`, and its state must exist before the capture (run at least one eager
-    step with the same optimizer object first): state created inside a capture is re-initialised by every replay;
+  * the optimizer must keep everything it reads on the device (`optim.FusedAdamW` does; `torch.optim.AdamW` needs
+    `capturable=True`), and its state must exist before the capture (run at least one eager step with the same optimizer object
+    first): state created inside a capture is re-initialised by every replay;
+  * gradient addresses must not change between the eager warm-up and the capture: `FusedAdamW` reads gradients through a
+    device-side pointer table built by the warm-up step, so zero gradients in place (`zero_grad(set_to_none=False)`, or the
+    fixed grad views of `parallel.GradientBucketer`); `FusedAdamW.step()` raises under capture if a gradient moved;
   * inputs are static buffers: copy each batch into one of the buffers that were captured, then `replay(buffer)`;
   * decoder dropout: the kernels take their seeds as host-side arguments (drawn from torch's CPU generator per call), so a
     captured step would replay the SAME keep masks every iteration — `ops.new_dropout_seeds` refuses to run under capture:

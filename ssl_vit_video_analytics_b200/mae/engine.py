@@ -56,7 +56,10 @@ def build_scheduler(cfg: Dict[str, Any], optimizer: torch.optim.Optimizer):
 
 
 def train_one_epoch(epoch: int, model: nn.Module, loader, optimizer: torch.optim.Optimizer, scaler, scheduler, device: torch.device,
-                    cfg: Dict[str, Any], logger) -> Dict[str, float]:
+                    cfg: Dict[str, Any], logger, loss_fn=None) -> Dict[str, float]:
+    """`loss_fn(pred, target, loss_type=..., normalize_target=...)` defaults to `losses.mae_recon_loss` (the sm_100a row-loss
+    kernels, CUDA only); the host-logic tests of this loop pass the CPU oracle's loss instead."""
+    loss_fn = loss_fn or mae_recon_loss
     model.train()
     training, mae_cfg, model_cfg = cfg.get("training", {}), cfg.get("mae", {}), cfg.get("model", {})
     log_interval = int(training.get("log_interval", 20))
@@ -90,7 +93,7 @@ def train_one_epoch(epoch: int, model: nn.Module, loader, optimizer: torch.optim
 
         with torch.amp.autocast(device_type=device.type, enabled=amp and device.type == "cuda"):
             pred, target = model(clip, token_mask)
-            loss = mae_recon_loss(pred, target, loss_type=loss_type, normalize_target=normalize_target)
+            loss = loss_fn(pred, target, loss_type=loss_type, normalize_target=normalize_target)
 
         if not torch.isfinite(loss):
             logger.write(f"[WARN] epoch={epoch} step={step} loss is not finite: {float(loss)} -> skip step")

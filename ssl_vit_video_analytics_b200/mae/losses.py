@@ -1,50 +1,45 @@
 """Drop-in for `src/mae/losses.py` (:19-144): latent-space MAE losses on gathered rows [N_mask, D].
 Per-row normalisation uses the BIASED variance and eps=1e-6 inside the sqrt (:36-38). CUDA tensors go to the fused row-loss
 kernels (`vmae_row_loss_fwd/bwd`: one pass for statistics + loss, one for the gradient; the target is detached, as at the
-reference's call site tinyvit_mae.py:112). CPU tensors keep the reference's tensor-op formulation (the reference's losses are
-device-agnostic and its CPU tests call them); the pixel-space loss of the training step is `ops.masked_mse`."""
+reference's call site tinyvit_mae.py:112). There is no CPU path: CPU tensors raise. The pixel-space loss of the training step
+is `ops.masked_mse`."""
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 
-def _normalise_rows(t: torch.Tensor) -> torch.Tensor:
-    mu = t.mean(dim=-1, keepdim=True)
-    var = t.var(dim=-1, keepdim=True, unbiased=False)
-    return (t - mu) / (var + 1.0e-6).sqrt()
-
-
-def _on_gpu(pred, target) -> bool:
-    return pred.is_cuda and target.is_cuda and pred.dim() == 2 and pred.shape == target.shape and not target.requires_grad
+def _rows(pred: torch.Tensor, target: torch.Tensor):
+    """The losses run on the sm_100a row-loss kernels only: CUDA tensors of equal shape, viewed as [rows, last dim]. The
+    target is a constant of the loss (the reference's call site passes `tok[mask].detach()`, tinyvit_mae.py:113-114)."""
+    if not (pred.is_cuda and target.is_cuda):
+        raise RuntimeError("ssl_vit_video_analytics_b200.mae.losses run on CUDA (sm_100a) tensors only; there is no CPU path")
+    if pred.shape != target.shape:
+        raise ValueError(f"pred {tuple(pred.shape)} and target {tuple(target.shape)} must have the same shape")
+    if target.requires_grad:
+        raise RuntimeError("the fused row losses treat the target as a constant: pass target.detach()")
+    d = pred.shape[-1]
+    return pred.reshape(-1, d), target.reshape(-1, d)
 
 
 def mae_l2_loss(pred: torch.Tensor, target: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-    if _on_gpu(pred, target):
-        from .. import ops
+    from .. import ops
 
-        return ops.row_loss(pred, target, 0, normalize, 1.0e-6)
-    if normalize:
-        target = _normalise_rows(target)
-    return ((pred - target) ** 2).mean()
+    p, t = _rows(pred, target)
+    return ops.row_loss(p, t, 0, normalize, 1.0e-6)
 
 
 def mae_l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    if _on_gpu(pred, target):
-        from .. import ops
+    from .. import ops
 
-        return ops.row_loss(pred, target, 1, False, 0.0)
-    return (pred - target).abs().mean()
+    p, t = _rows(pred, target)
+    return ops.row_loss(p, t, 1, False, 0.0)
 
 
 def mae_cosine_loss(pred: torch.Tensor, target: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    if _on_gpu(pred, target):
-        from .. import ops
+    from .. import ops
 
-        return ops.row_loss(pred, target, 2, False, eps)
-    p = F.normalize(pred, dim=-1, eps=eps)
-    t = F.normalize(target, dim=-1, eps=eps)
-    return 1.0 - (p * t).sum(dim=-1).mean()
+    p, t = _rows(pred, target)
+    return ops.row_loss(p, t, 2, False, eps)
 
 
 def build_mae_loss(pred: torch.Tensor, target: torch.Tensor, loss_type: str = "l2", normalize: bool = True) -> torch.Tensor:

@@ -123,9 +123,14 @@ class TinyVideoMAE(nn.Module):
 
     def forward(self, x, mask):
         """x: [B, 3, T, H, W] float; mask: [B, T, L] bool (True = masked) -> pred [B, T*L, 192]."""
+        if not x.is_cuda:
+            raise RuntimeError("TinyVideoMAE runs on CUDA (sm_100a) tensors only; there is no CPU path")
+        with ops.weight_cache_scope(self):   # one launch: bf16 operand copies of every weight matrix, valid for this forward
+            return self._forward(x, mask)
+
+    def _forward(self, x, mask):
         B, Cc, T, H, W = x.shape
         Lp = self.num_patches
-        ops.refresh_weight_cache(self)   # one launch: bf16 operand copies of every weight matrix
         frames = x.permute(0, 2, 1, 3, 4).flatten(0, 1)
         latent = self.encoder.forward_stage3(frames)                       # [B*T, 384, S/8, S/8]
         tok = latent.permute(0, 2, 3, 1).reshape(B * T * Lp, self.encoder_dim)

@@ -1,12 +1,13 @@
 """Drop-in for the reference encoder `src/models/tiny_vit.py` (constructors, forward signatures and state_dict keys
 unchanged; file:line citations refer to that file).
 
-Transformer parts (Attention :86-106, Mlp :74-84, TinyViTBlock :108-130) run on the hand-written sm_100a kernels
-(tcgen05 GEMMs with fused epilogues, tcgen05 flash attention, warp-shuffle LayerNorm) through `ops`. In the convolutional
-stages (Conv2d_BN :12-18, SELayer :20-34, MBConv :36-56, PatchEmbed :62-72) the point-wise (1x1) convolutions and the
-squeeze-excite Linears run on the same GEMM over the channels-last view of the feature map; the 3x3 stem / depthwise
-convolutions, BatchNorm statistics and elementwise activations keep the reference arithmetic and key layout and are
-still dispatched by PyTorch in this round (the rest of the K7 row of SURVEY.md §2b).
+Every layer runs on the hand-written sm_100a kernels through `ops`; feature maps are channels-last bf16 internally.
+Transformer parts (Attention :86-106, Mlp :74-84, TinyViTBlock :108-130): tcgen05 GEMMs with fused epilogues, tcgen05
+flash attention, warp-shuffle LayerNorm. Convolutional stages (Conv2d_BN :12-18, SELayer :20-34, MBConv :36-56,
+PatchEmbed :62-72): 1x1 convolutions and the squeeze-excite Linears on the same GEMM over rows = pixels, the 3x3 stem
+convolutions as im2col + GEMM, depthwise 3x3 on the TMA-staged depthwise kernel, BatchNorm (train-mode batch statistics
+with running-stat update; eval-mode running statistics) with the following GELU and the MBConv residual fused into its
+apply pass. CPU tensors and layer configurations without a kernel raise — there is no fallback path.
 """
 from __future__ import annotations
 
@@ -19,19 +20,26 @@ from .. import ops
 
 
 class DropPath(nn.Module):
-    """Per-sample stochastic depth (the reference imports timm.layers.DropPath, tiny_vit.py:5)."""
+    """Per-sample stochastic depth (the reference imports timm.layers.DropPath, tiny_vit.py:5). `keep_override` (a list of
+    0/1 tensors [B], used cyclically call by call) replaces the Bernoulli draw: parity tests feed both sides the same masks."""
 
     def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True):
         super().__init__()
         self.drop_prob = float(drop_prob)
         self.scale_by_keep = scale_by_keep
+        self.keep_override = None
+        self._calls = 0
 
     def forward(self, x):
         if self.drop_prob == 0.0 or not self.training:
             return x
         keep = 1.0 - self.drop_prob
         shape = (x.shape[0],) + (1,) * (x.ndim - 1)
-        mask = x.new_empty(shape).bernoulli_(keep)
+        if self.keep_override is not None:
+            mask = self.keep_override[self._calls % len(self.keep_override)].to(device=x.device, dtype=x.dtype).reshape(shape).clone()
+            self._calls += 1
+        else:
+            mask = x.new_empty(shape).bernoulli_(keep)
         if keep > 0.0 and self.scale_by_keep:
             mask.div_(keep)
         return x * mask
@@ -101,20 +109,24 @@ class Conv2d_BN(nn.Sequential):
         return ops.LinearFn.apply(col, w2d, None, L.ACT_NONE), (n, ho, wo)
 
     def forward(self, x, act=False, residual=None):
-        kind = self._kind() if x.is_cuda else None
+        if not x.is_cuda:
+            raise RuntimeError("Conv2d_BN runs on CUDA (sm_100a) tensors only; there is no CPU path")
+        kind = self._kind()
         bn = self.bn
-        if kind is None or not bn.training or bn.momentum is None or not bn.track_running_stats:
-            # eval-mode statistics / exotic configurations keep the reference ops
-            y = bn(self.c(x))
-            if act:
-                y = torch.nn.functional.gelu(y)
-            return y if residual is None else y + residual
+        if kind is None:
+            raise RuntimeError(f"Conv2d_BN: no sm_100a kernel for {self.c} (supported: 1x1 s1, 3x3 pad 1 stride 1|2 dense or "
+                               f"depthwise, channels a multiple of 8, dilation 1)")
+        if bn.momentum is None or not bn.track_running_stats:
+            raise RuntimeError("Conv2d_BN: BatchNorm2d without running statistics / with cumulative momentum is not supported")
         rows, (n, ho, wo) = self._conv_rows(x, kind)
         res_rows = ops.as_nhwc_bf16(residual).view(rows.shape) if residual is not None else None
-        y = ops.BatchNormActFn.apply(rows, bn.weight, bn.bias, bn.running_mean, bn.running_var, res_rows, bn.eps, bn.momentum,
-                                     L.ACT_GELU if act else L.ACT_NONE)
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
+        a = L.ACT_GELU if act else L.ACT_NONE
+        if bn.training:
+            y = ops.BatchNormActFn.apply(rows, bn.weight, bn.bias, bn.running_mean, bn.running_var, res_rows, bn.eps, bn.momentum, a)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+        else:   # eval(): running statistics, same apply kernel (vmae_bn_apply)
+            y = ops.BatchNormEvalFn.apply(rows, bn.weight, bn.bias, bn.running_mean, bn.running_var, res_rows, bn.eps, a)
         return _nchw_view(y.view(n, ho, wo, -1))
 
 
@@ -133,21 +145,17 @@ class SELayer(nn.Module):
 
     def forward(self, x):
         n, c = x.shape[0], x.shape[1]
-        if x.is_cuda and c % 32 == 0:
-            # pool / gating kernels on the channels-last rows; the two bias-free Linears on the tcgen05 GEMM; ReLU and
-            # sigmoid are elementwise glue on the tiny [n, c/4] and [n, c] tensors
-            xr = ops.as_nhwc_bf16(x)
-            h_, w_ = xr.shape[1], xr.shape[2]
-            rows = xr.view(n, h_ * w_, c)
-            pooled = ops.SEPoolFn.apply(rows)
-            hid = torch.relu(ops.cast_f32_autograd(ops.LinearFn.apply(pooled, self.fc[0].weight, None, L.ACT_NONE)))
-            gate = torch.sigmoid(ops.cast_f32_autograd(ops.LinearFn.apply(hid, self.fc[2].weight, None, L.ACT_NONE)))
-            y = _nchw_view(ops.SEScaleFn.apply(rows, gate).view(n, h_, w_, c))
-            if x.dtype != ops.BF16:   # eval-mode neighbours run the reference ops in the caller's dtype
-                y = ops.cast_f32_autograd(y.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2).to(x.dtype)
-            return y
-        gate = self.fc(self.avg_pool(x).view(n, c))
-        return x * gate.view(n, c, 1, 1).expand_as(x)
+        if not x.is_cuda or c % 32 != 0:
+            raise RuntimeError("SELayer runs on CUDA (sm_100a) feature maps with a multiple of 32 channels; there is no fallback path")
+        # pool / gating kernels on the channels-last rows; the two bias-free Linears on the tcgen05 GEMM; ReLU and
+        # sigmoid are elementwise glue on the tiny [n, c/4] and [n, c] tensors
+        xr = ops.as_nhwc_bf16(x)
+        h_, w_ = xr.shape[1], xr.shape[2]
+        rows = xr.view(n, h_ * w_, c)
+        pooled = ops.SEPoolFn.apply(rows)
+        hid = torch.relu(ops.cast_f32_autograd(ops.LinearFn.apply(pooled, self.fc[0].weight, None, L.ACT_NONE)))
+        gate = torch.sigmoid(ops.cast_f32_autograd(ops.LinearFn.apply(hid, self.fc[2].weight, None, L.ACT_NONE)))
+        return _nchw_view(ops.SEScaleFn.apply(rows, gate).view(n, h_, w_, c))
 
 
 class MBConv(nn.Module):
@@ -317,17 +325,19 @@ class TinyViT(nn.Module):
 
     def forward_stage3(self, x):
         """MAE pre-training interface: stem + stages 0..2 -> [BT, 384, S/8, S/8] (tiny_vit.py:166-176)."""
-        x = self.patch_embed(x)
-        for s in range(3):
-            x = self._run_stage(self.stages[s], x)
-        return self._boundary(x)
+        with ops.weight_cache_scope(self):
+            x = self.patch_embed(x)
+            for s in range(3):
+                x = self._run_stage(self.stages[s], x)
+            return self._boundary(x)
 
     def forward(self, x):
         """Classification / finetune interface: all four stages (tiny_vit.py:178-186)."""
-        x = self.patch_embed(x)
-        for stage in self.stages:
-            x = self._run_stage(stage, x)
-        return self._boundary(x)
+        with ops.weight_cache_scope(self):
+            x = self.patch_embed(x)
+            for stage in self.stages:
+                x = self._run_stage(stage, x)
+            return self._boundary(x)
 
 
 def tiny_vit_21m_variant(img_size=112, use_checkpoint=True, **kwargs):

@@ -115,7 +115,14 @@ class VideoMAEViT(nn.Module):
         n_vis defaults to the count in clip 0 (one host sync); pass it to stay sync-free (CUDA-graph capture)."""
         frame = mask[:, 0].to(torch.uint8).contiguous()
         if n_vis is None:
-            n_vis = int((frame[0] == 0).sum().item())
+            # one host sync anyway: also check that this IS a tube mask with the same visible count in every clip (a
+            # `make_token_mask(mode="random")` mask would give the encoder and the decoder different token sets)
+            counts = (frame == 0).sum(dim=1)
+            ok = bool(((mask == mask[:, :1]).all() & (counts == counts[0]).all()).item())
+            if not ok:
+                raise ValueError("VideoMAEViT needs a tube mask (identical over T') with the same number of visible patches in "
+                                 "every clip, e.g. datasets.mae_loader.get_tube_mask")
+            n_vis = int(counts[0].item())
         return ops.mask_to_indices(frame, n_vis)
 
     def forward(self, x, mask, vis_idx=None):
@@ -128,7 +135,10 @@ class VideoMAEViT(nn.Module):
         x = x.contiguous()
         if vis_idx is None:
             vis_idx = self.visible_indices(mask)
-        ops.refresh_weight_cache(self)   # one launch: bf16 operand copies of every weight matrix
+        with ops.weight_cache_scope(self):   # one launch: bf16 operand copies of every weight matrix, valid for this forward
+            return self._forward_tokens(x, mask, vis_idx, B, Tp, Lp, pt, ps)
+
+    def _forward_tokens(self, x, mask, vis_idx, B, Tp, Lp, pt, ps):
         n_vis = vis_idx.shape[1]
         Lv = Tp * n_vis
         patches, pos_rows = ops.TubeletGatherFn.apply(x, vis_idx, self.enc_temporal_pos_embed, self.enc_spatial_pos_embed, pt, ps)

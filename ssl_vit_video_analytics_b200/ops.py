@@ -201,7 +201,7 @@ _WEIGHT_BF16 = {}
 
 
 def cast_weight(w: torch.Tensor) -> torch.Tensor:
-    """bf16 GEMM operand of a weight: the WeightCache copy if the owning model refreshed it this step, else a cast."""
+    """bf16 GEMM operand of a weight: the WeightCache copy while the owning model's forward scope is open, else a cast."""
     e = _WEIGHT_BF16.get(id(w))
     if e is not None and e[0]() is w and e[1].device == w.device:   # identity check: ids are recycled after a model dies
         return e[1]
@@ -237,16 +237,52 @@ class WeightCache:
         for p, c in zip(self.params, self.copies):
             _WEIGHT_BF16[id(p)] = (weakref.ref(p), c)
 
+    def release(self) -> None:
+        for p in self.params:
+            _WEIGHT_BF16.pop(id(p), None)
 
-def refresh_weight_cache(module: torch.nn.Module) -> None:
-    """Called by the models at the start of forward on CUDA: (re)build the cache if parameters moved, then one launch."""
+
+def refresh_weight_cache(module: torch.nn.Module):
+    """(Re)build the module's cache if parameters moved, then one launch that refreshes every bf16 copy. Returns the cache."""
     cache = module.__dict__.get("_vmae_weight_cache")
     if cache is None or cache.stale():
         if not any(p.is_cuda for p in module.parameters()):
-            return
+            return None
         cache = WeightCache(module)
         module.__dict__["_vmae_weight_cache"] = cache
     cache.refresh()
+    return cache
+
+
+_SCOPE_DEPTH = 0
+
+
+class weight_cache_scope:
+    """`with weight_cache_scope(model):` around a model's forward. The OUTERMOST scope refreshes the bf16 copies of all of the
+    model's weight matrices with one launch and publishes them to `cast_weight`; nested scopes (an encoder called by the MAE
+    wrapper) reuse them. On exit the copies are withdrawn, so a weight is never served from a copy made before the last
+    optimizer step: outside a scope (a bare sub-module call, an activation-checkpoint recompute) `cast_weight` casts afresh.
+    Backward is unaffected: the autograd Functions save the bf16 operands they used."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = module
+        self.cache = None
+        self.owner = False
+
+    def __enter__(self):
+        global _SCOPE_DEPTH
+        self.owner = _SCOPE_DEPTH == 0
+        _SCOPE_DEPTH += 1
+        if self.owner:
+            self.cache = refresh_weight_cache(self.module)
+        return self
+
+    def __exit__(self, *exc):
+        global _SCOPE_DEPTH
+        _SCOPE_DEPTH -= 1
+        if self.owner and self.cache is not None:
+            self.cache.release()
+        return False
 
 
 def cast_f32(x: torch.Tensor) -> torch.Tensor:
@@ -526,13 +562,30 @@ _GRAD_SHADOW = [None]
 def _shadow_key(t):
     return (t.data_ptr(), t.numel())
 
-# When a parameter already owns a contiguous fp32 .grad (e.g. a view into a GradientBucketer bucket), the fused block
-# accumulates into it directly (TMA reduce-add / red.add) and returns None to autograd: no zero-filled temporary, no
-# extra "grad += new" pass. GRAD_READY_HOOK(param) replaces the post-accumulate hook autograd would have fired.
+# Direct gradient accumulation (opt-in). For a parameter marked by `enable_direct_grad(params, hook)` that already owns a contiguous
+# fp32 .grad (e.g. a view into a GradientBucketer bucket) the fused block accumulates into it in place (TMA reduce-add / red.add)
+# and returns None to autograd: no zero-filled temporary, no extra "grad += new" pass. Because autograd then never sees that
+# gradient, tensor hooks do not fire and `torch.autograd.grad(...)` would get None — hence opt-in, by whoever owns the .grad
+# buffers and calls `.backward()`. `hook(param)` (per parameter, not one global) replaces the post-accumulate hook autograd
+# would have fired. GRAD_READY_HOOK is an additional process-wide observer (tests).
 GRAD_READY_HOOK = None
 
 
+def enable_direct_grad(params, hook=None) -> None:
+    for p in params:
+        p._vmae_direct_grad = True
+        p._vmae_grad_hook = hook
+
+
+def disable_direct_grad(params) -> None:
+    for p in params:
+        p._vmae_direct_grad = False
+        p._vmae_grad_hook = None
+
+
 def _direct_grad(p):
+    if not getattr(p, "_vmae_direct_grad", False):
+        return None
     g = getattr(p, "grad", None)
     if g is not None and g.dtype == F32 and g.is_contiguous() and g.shape == p.shape and g.is_cuda:
         return g
@@ -540,8 +593,27 @@ def _direct_grad(p):
 
 
 def _grad_done(p):
+    h = getattr(p, "_vmae_grad_hook", None)
+    if h is not None:
+        h(p)
     if GRAD_READY_HOOK is not None:
         GRAD_READY_HOOK(p)
+
+
+_SHADOW_CB = [False]
+
+
+def _clear_shadow():
+    _GRAD_SHADOW[0] = None
+    _SHADOW_CB[0] = False
+
+
+def _publish_shadow(dx, dx_b):
+    """Hand (dx, bf16 copy) to the next block's backward; dropped when this backward pass ends (no reference outlives it)."""
+    _GRAD_SHADOW[0] = (_shadow_key(dx), dx, dx_b)
+    if not _SHADOW_CB[0]:
+        _SHADOW_CB[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_clear_shadow)
 
 
 class TransformerBlockFn(torch.autograd.Function):
@@ -625,7 +697,7 @@ class TransformerBlockFn(torch.autograd.Function):
         dln1 = linear_dgrad(dqkv, wq)
         dwq, dbq = linear_wgrad_bias(dqkv, ln1, t_wq, t_bq)
         dx, dx_b, dg1, dbeta1 = layernorm_bwd(dln1, x, ln1_w, mean1, rstd1, dx_resid=dx1, dgamma=t_g1, dbeta=t_b1, want_bf16=True)
-        _GRAD_SHADOW[0] = (_shadow_key(dx), dx, dx_b)
+        _publish_shadow(dx, dx_b)
         grads = [dg1, dbeta1, dwq, dbq, dwp, dbp, dg2, dbeta2, dw1, db1, dw2, db2]
         out = []
         # reverse order ~ the order in which the gradients became final (fc2 first), so buckets close as early as possible
@@ -847,22 +919,156 @@ def row_loss(pred, target, mode, normalize=True, eps=1e-6):
     return RowLossFn.apply(pred, target, mode, normalize, eps)
 
 
+# ---- stack 2 (tinyvit_mae.py:104-114): mask-token substitution and the boolean row gathers, sync-free ---------------------
+def mask_row_indices(mask_u8, n_sel, want=1, flag=None):
+    """mask uint8 [B, N] -> int32 [B * n_sel] global row numbers (b*N + n) of the entries with (mask != 0) == want, ascending:
+    the row order of `x[mask]`. `flag` (int32 scalar on the device, zeroed by the caller) records a per-clip count mismatch."""
+    B, N = mask_u8.shape
+    idx = torch.empty((B * n_sel,), device=mask_u8.device, dtype=torch.int32)
+    L.check(L.load().vmae_mask_row_indices(_p(mask_u8), _p(idx), _p(flag), B, N, int(n_sel), int(want), _stream()), "vmae_mask_row_indices")
+    _count()
+    return idx
+
+
+class MaskTokenBlendFn(torch.autograd.Function):
+    """torch.where(mask[..., None], mask_token, tok) (tinyvit_mae.py:107-108). tok [B, N, D] bf16/fp32; mask uint8 [B, N]."""
+
+    @staticmethod
+    def forward(ctx, tok, mask_u8, mask_token):
+        _need_cuda(tok, mask_u8, mask_token)
+        tok = tok.contiguous()
+        if tok.dtype not in (BF16, F32):
+            tok = tok.float()
+        D = tok.shape[-1]
+        rows = tok.numel() // D
+        out = torch.empty_like(tok)
+        mt = mask_token.reshape(D).float().contiguous()
+        L.check(L.load().vmae_mask_token_blend_fwd(_p(tok), _dt(tok), _p(mask_u8), _p(mt), _p(out), rows, D, _stream()), "vmae_mask_token_blend_fwd")
+        _count()
+        ctx.save_for_backward(mask_u8)
+        ctx.mt_shape = mask_token.shape
+        ctx.mt_dtype = mask_token.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask_u8,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        D = dout.shape[-1]
+        rows = dout.numel() // D
+        dtok = torch.empty_like(dout) if ctx.needs_input_grad[0] else None
+        dmt = torch.zeros((D,), device=dout.device, dtype=F32) if ctx.needs_input_grad[2] else None
+        L.check(L.load().vmae_mask_token_blend_bwd(_p(dout), _dt(dout), _p(mask_u8), _p(dtok), _p(dmt), rows, D, _stream()), "vmae_mask_token_blend_bwd")
+        _count()
+        return dtok, None, (dmt.reshape(ctx.mt_shape).to(ctx.mt_dtype) if dmt is not None else None)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """out[i, :] = src2d[idx[i], :]; backward scatters into zeros (the rows are unique)."""
+
+    @staticmethod
+    def forward(ctx, src, idx):
+        _need_cuda(src, idx)
+        D = src.shape[-1]
+        src2 = src.reshape(-1, D).contiguous()
+        if src2.dtype not in (BF16, F32):
+            src2 = src2.float()
+        out = torch.empty((idx.numel(), D), device=src.device, dtype=src2.dtype)
+        L.check(L.load().vmae_gather_rows(_p(src2), _dt(src2), _p(idx), _p(out), idx.numel(), D, _stream()), "vmae_gather_rows")
+        _count()
+        ctx.save_for_backward(idx)
+        ctx.src_shape = src.shape
+        ctx.n_rows = src2.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        D = dout.shape[-1]
+        dsrc = torch.empty((ctx.n_rows, D), device=dout.device, dtype=dout.dtype)
+        L.check(L.load().vmae_scatter_rows(_p(dout), _dt(dout), _p(idx), _p(dsrc), idx.numel(), ctx.n_rows, D, _stream()), "vmae_scatter_rows")
+        _count(2)
+        return dsrc.reshape(ctx.src_shape), None
+
+
+class AdaptiveAvgPoolFn(torch.autograd.Function):
+    """F.adaptive_avg_pool2d(f, (s, s)).flatten(2).transpose(1, 2) (tinyvit_backbone.py:74-81): bf16 NHWC [N,H,W,C] -> fp32 [N, s*s, C]."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, s):
+        _need_cuda(x_nhwc)
+        N, H, W, Cc = x_nhwc.shape
+        assert x_nhwc.dtype == BF16 and x_nhwc.is_contiguous()
+        out = torch.empty((N, s * s, Cc), device=x_nhwc.device, dtype=F32)
+        L.check(L.load().vmae_adaptive_avgpool_fwd(_p(x_nhwc), _p(out), N, H, W, Cc, int(s), _stream()), "vmae_adaptive_avgpool_fwd")
+        _count()
+        ctx.geom = (N, H, W, Cc, int(s))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, Cc, s = ctx.geom
+        dx = torch.empty((N, H, W, Cc), device=dout.device, dtype=BF16)
+        L.check(L.load().vmae_adaptive_avgpool_bwd(_p(dout.float().contiguous()), _p(dx), N, H, W, Cc, s, _stream()), "vmae_adaptive_avgpool_bwd")
+        _count()
+        return dx, None
+
+
+class SoftmaxCrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss (mean) on logits [rows, C] bf16/fp32 and int64 labels, fused: one pass for lse + loss, one for dlogits."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _need_cuda(logits, labels)
+        assert logits.dim() == 2 and labels.shape == (logits.shape[0],)
+        lg = logits.contiguous()
+        if lg.dtype not in (BF16, F32):
+            lg = lg.float()
+        lb = labels.to(torch.int64).contiguous()
+        rows, Cn = lg.shape
+        lse = torch.empty((rows,), device=lg.device, dtype=F32)
+        row_loss = torch.empty((rows,), device=lg.device, dtype=F32)
+        loss = torch.empty((), device=lg.device, dtype=F32)
+        L.check(L.load().vmae_softmax_ce_fwd(_p(lg), _dt(lg), _p(lb), _p(lse), _p(row_loss), _p(loss), rows, Cn, _stream()), "vmae_softmax_ce_fwd")
+        _count(2)
+        ctx.save_for_backward(lg, lb, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lg, lb, lse = ctx.saved_tensors
+        rows, Cn = lg.shape
+        dl = torch.empty_like(lg)
+        g = gout.detach().reshape(1).float().contiguous()
+        L.check(L.load().vmae_softmax_ce_bwd(_p(lg), _dt(lg), _p(lb), _p(lse), _p(g), _p(dl), rows, Cn, _stream()), "vmae_softmax_ce_bwd")
+        _count()
+        return dl, None
+
+
+def softmax_cross_entropy(logits, labels):
+    return SoftmaxCrossEntropyFn.apply(logits, labels)
+
+
 class GaussianNoiseFn(torch.autograd.Function):
     """z' = z + sigma * eps, eps ~ N(0, I) from Philox (privacy/feature_noise.py:4-7); gradient is the identity."""
 
     @staticmethod
-    def forward(ctx, z, sigma, seed, offset):
+    def forward(ctx, z, sigma, seed, offset, eps_out=None):
+        """eps_out (optional fp32 tensor of z's shape) receives the unit normals that were drawn: out == z + sigma * eps_out."""
         _need_cuda(z)
         zc = z.contiguous()
         out = torch.empty_like(zc)
-        L.check(L.load().vmae_add_gaussian_noise(_p(zc), _p(out), _dt(zc), None, zc.numel(), float(sigma), int(seed), int(offset),
+        if eps_out is not None:
+            assert eps_out.dtype == F32 and eps_out.is_contiguous() and eps_out.numel() == zc.numel() and eps_out.is_cuda
+        L.check(L.load().vmae_add_gaussian_noise(_p(zc), _p(out), _dt(zc), _p(eps_out), zc.numel(), float(sigma), int(seed), int(offset),
                                                  _stream()), "vmae_add_gaussian_noise")
         _count()
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None, None
+        return g, None, None, None, None
 
 
 def scale_f32(x, alpha, out=None, accumulate=False):
@@ -923,6 +1129,30 @@ class BatchNormActFn(torch.autograd.Function):
             _p(x), _p(dy), _p(g), _p(b), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), M, Cc, ctx.act, _stream())), "vmae_bn_train_bwd")
         _count(2)
         return dx, dg, db, None, None, (dy if ctx.has_res else None), None, None, None
+
+
+class BatchNormEvalFn(torch.autograd.Function):
+    """Eval-mode BatchNorm2d over rows [M, C] with the running statistics (+ optional exact GELU, + optional residual):
+    `vmae_bn_apply`. Inference only — the backward of the eval form is not part of the training path and raises."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, act):
+        _need_cuda(x, gamma)
+        M, Cc = x.shape
+        g, b = gamma.float().contiguous(), beta.float().contiguous()
+        mean = running_mean.float().contiguous()
+        rstd = torch.rsqrt(running_var.float() + eps).contiguous()       # [C] glue
+        y = torch.empty_like(x)
+        nbytes = float(M) * Cc * 2 * (2 + (1 if residual is not None else 0))
+        L.check(_run("batchnorm_fwd", nbytes, lambda: L.load().vmae_bn_apply(
+            _p(x), _p(g), _p(b), _p(mean), _p(rstd), _p(residual), _p(y), M, Cc, int(act), _stream())), "vmae_bn_apply")
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        raise RuntimeError("eval-mode BatchNorm (running statistics) has no backward on the sm_100a path: call model.train() to "
+                           "train (the reference trains with batch statistics, tiny_vit.py:12-18)")
 
 
 class DepthwiseConv3x3Fn(torch.autograd.Function):

@@ -2,7 +2,9 @@
 `src/train_ssl_mae.py:163`, `src/mae/engine.py` via `build_optimizer`).
 
 Same constructor arguments, `param_groups`, `state` and update rule as `torch.optim.AdamW` (decoupled weight decay, bias
-correction with the per-parameter step count); the difference is where things live: every hyper-parameter the update reads
+correction — with ONE step count per parameter group where torch keeps one per tensor; the two differ only for a parameter
+that starts receiving gradients later than its group, e.g. a backbone unfrozen by `two_stage` finetune: give such parameters
+their own group); the difference is where things live: every hyper-parameter the update reads
 (lr, betas, eps, weight decay, step) sits in a small device array per parameter group, and all tensors of a group are updated by
 ONE kernel launch through a device-side chunk table (`vmae_adamw_multi`). Nothing is read from the host at run time, so a step
 captured in a CUDA graph (graph_step.py) stays correct while a scheduler changes `param_groups[i]["lr"]` between replays — call
@@ -113,6 +115,17 @@ class FusedAdamW(torch.optim.Optimizer):
                 if capturing:
                     raise RuntimeError("FusedAdamW: run one eager step() before capturing (the chunk table and the state are built there)")
                 continue
+            if capturing:
+                # The chunk table was filled by the eager warm-up step and cannot be rebuilt inside a capture (it is an H2D
+                # copy). A captured step must therefore keep every gradient at the address the warm-up saw: use
+                # `zero_grad(set_to_none=False)` or `parallel.GradientBucketer` (fixed grad views). With the torch default
+                # `set_to_none=True`, backward would allocate fresh .grad tensors in the graph pool and every replay would
+                # apply AdamW to the stale warm-up gradients.
+                ps = plan["params"]
+                if any(p.grad is None for p in ps) or tuple(p.grad.data_ptr() for p in ps) != plan["gkey"]:
+                    raise RuntimeError(
+                        "FusedAdamW.step() inside a CUDA-graph capture: a gradient is missing or has moved since the eager warm-up "
+                        "step. Keep gradient addresses fixed in a captured step (zero_grad(set_to_none=False) or GradientBucketer).")
             self.sync_hyperparameters()
             L.check(lib.vmae_adamw_multi(ops._p(plan["table"]), plan["chunks"], ops._p(plan["hp"]), ops._stream()), "vmae_adamw_multi")
             ops._count(2)

@@ -76,10 +76,10 @@ class GradientBucketer(nn.Module):
         # collectives stay outside the graph.
         self.defer_comm = False
         if self.on_cuda:
-            # fused blocks that accumulate straight into the bucket views report completion through this hook
+            # fused blocks accumulate straight into the bucket views of THESE parameters and report completion per parameter
             from . import ops
 
-            ops.GRAD_READY_HOOK = self._on_direct_grad
+            ops.enable_direct_grad([p for b in self.buckets for p in b.params], self._on_direct_grad)
 
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, *args, **kwargs):

@@ -9,13 +9,15 @@ from .. import ops
 _offset = 0
 
 
-def add_gaussian_noise(z, sigma, seed=None):
+def add_gaussian_noise(z, sigma, seed=None, eps_out=None):
+    """`eps_out` (optional, fp32, z's shape, CUDA) receives the normals that were drawn, so that `out == z + sigma * eps_out`
+    can be checked exactly (the parity contract of SURVEY.md §8 a19)."""
     global _offset
     if sigma <= 0:
         return z
     if seed is None:
         seed = torch.initial_seed()
-    out = ops.GaussianNoiseFn.apply(z, float(sigma), int(seed) & 0xFFFFFFFFFFFFFFFF, _offset)
+    out = ops.GaussianNoiseFn.apply(z, float(sigma), int(seed) & 0xFFFFFFFFFFFFFFFF, _offset, eps_out)
     _offset += (z.numel() + 3) // 4
     return out
 

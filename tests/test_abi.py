@@ -44,7 +44,7 @@ def test_ctypes_table_mirrors_header():
 
 def test_argument_validation_fails_loudly():
     lib = _lib.load()
-    assert lib.vmae_abi_version() == 2
+    assert lib.vmae_abi_version() == 3
     rc = lib.vmae_layernorm_fwd(None, 1, None, None, None, 0, None, None, 4, 384, 1e-5, None)
     assert rc == -1 and b"null" in lib.vmae_last_error()
     rc = lib.vmae_gemm_bf16(None, 0, 0, None, 0, 0, 128, 64, 64, None, None, 0, None, 0, None, 0, None, 0, 0, 0, 0, 1, None)

@@ -4,6 +4,7 @@ import math
 
 import torch
 
+from oracle import restatement as R
 from ssl_vit_video_analytics_b200.mae import engine as E
 
 
@@ -74,7 +75,7 @@ def test_epoch_semantics_accumulation_clip_skip_and_schedule():
 
     log = Log()
     w0 = model.lin.weight.detach().clone()
-    out = E.train_one_epoch(1, model, _loader(6), opt, None, Sch(), torch.device("cpu"), cfg, log)
+    out = E.train_one_epoch(1, model, _loader(6), opt, None, Sch(), torch.device("cpu"), cfg, log, loss_fn=R.mae_recon_loss)
     # 6 batches, accumulation 2 -> optimizer steps after batches 1, 3, 5; batch 2 is non-finite: skipped (gradients cleared), so the step
     # after batch 3 carries only batch 3's gradient; the scheduler steps with the optimizer
     assert steps == {"opt": 3, "sch": 3}
@@ -83,7 +84,7 @@ def test_epoch_semantics_accumulation_clip_skip_and_schedule():
     assert not torch.equal(w0, model.lin.weight)
     m = model.seen_masks[0]
     assert m.shape == (2, 4 * 9) and int(m[0].sum()) == 4 * max(1, round(9 * 0.25))     # tube mask: same patches in every frame
-    out3 = E.train_one_epoch(3, StubMAE(), _loader(2), opt, None, None, torch.device("cpu"), cfg, Log())
+    out3 = E.train_one_epoch(3, StubMAE(), _loader(2), opt, None, None, torch.device("cpu"), cfg, Log(), loss_fn=R.mae_recon_loss)
     assert out3["mask_ratio"] == 0.75
 
 
@@ -92,7 +93,7 @@ def test_gradient_clipping_bounds_the_update():
     model = StubMAE()
     opt = torch.optim.SGD(model.parameters(), lr=1.0)
     w0 = torch.cat([p.detach().flatten().clone() for p in model.parameters()])
-    E.train_one_epoch(1, model, _loader(1), opt, None, None, torch.device("cpu"), cfg, Log())
+    E.train_one_epoch(1, model, _loader(1), opt, None, None, torch.device("cpu"), cfg, Log(), loss_fn=R.mae_recon_loss)
     w1 = torch.cat([p.detach().flatten() for p in model.parameters()])
     assert float((w1 - w0).norm()) <= 1e-3 * 1.0001           # SGD with lr 1: the step is the clipped gradient
 

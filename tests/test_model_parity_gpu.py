@@ -181,11 +181,11 @@ def test_second_backward_accumulates_directly_into_grad_buffers():
     g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
     ptrs = {k: p.grad.data_ptr() for k, p in model.named_parameters()}
     seen = []
-    ops.GRAD_READY_HOOK = lambda p: seen.append(p)
+    ops.enable_direct_grad(list(model.parameters()), lambda p: seen.append(p))     # opt-in, as GradientBucketer does
     try:
         model.training_loss(clip_d, mask_d, vis).backward()
     finally:
-        ops.GRAD_READY_HOOK = None
+        ops.disable_direct_grad(list(model.parameters()))
     assert len(seen) == 12 * (cfg["model"]["depth"] + cfg["model"]["decoder_depth"])
     for k, p in model.named_parameters():
         assert p.grad.data_ptr() == ptrs[k]
@@ -262,7 +262,7 @@ def test_finetune_classifier_vs_oracle():
     assert apply_finetune_mode(model, "ft_ssl") is True
     with torch.autocast("cuda", dtype=torch.bfloat16):
         logits = model(clip.cuda())
-    loss = F.cross_entropy(logits.float(), labels.cuda())
+    loss = model.loss(logits, labels.cuda())                           # fused softmax cross-entropy kernel
     loss.backward()
     assert abs(float(loss) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o)) + 1e-3
     assert cosine(logits.detach().float().cpu(), logits_o.detach()) > 0.999

@@ -102,21 +102,23 @@ def test_patchify_layout(host):
 
 
 def test_stack2_losses(host):
+    """The oracle's losses against the live-reference golden values; ours are CUDA-only (checked against the same goldens in
+    tests/test_kernels_gpu.py) and must refuse CPU tensors."""
     from ssl_vit_video_analytics_b200.mae import losses
 
     p, t = host["loss_inputs"]
-    assert torch.allclose(losses.mae_l2_loss(p, t, True), host["mae_l2_norm"], rtol=1e-6)
     assert torch.allclose(R.mae_l2_loss(p, t, True), host["mae_l2_norm"], rtol=1e-6)
-    assert torch.allclose(losses.mae_l2_loss(p, t, False), host["mae_l2_raw"], rtol=1e-6)
-    assert torch.allclose(losses.mae_l1_loss(p, t), host["mae_l1"], rtol=1e-6)
-    assert torch.allclose(losses.mae_cosine_loss(p, t), host["mae_cos"], rtol=1e-6)
-    assert torch.allclose(losses.mae_recon_loss(p, t, "l1", False), host["mae_recon_positional"], rtol=1e-6)
-    assert torch.allclose(losses.mae_recon_loss(p, t, normalize_target=True), host["mae_l2_norm"], rtol=1e-6)
+    assert torch.allclose(R.mae_l2_loss(p, t, False), host["mae_l2_raw"], rtol=1e-6)
+    assert torch.allclose(R.mae_l1_loss(p, t), host["mae_l1"], rtol=1e-6)
+    assert torch.allclose(R.mae_cosine_loss(p, t), host["mae_cos"], rtol=1e-6)
+    assert torch.allclose(R.mae_recon_loss(p, t, "l1", False), host["mae_recon_positional"], rtol=1e-6)
     stats = losses.reconstruction_error_stats(p, t)
     for k, v in host["recon_stats"].items():
         assert stats[k] == pytest.approx(v, rel=1e-6)
-    with pytest.raises(ValueError):
-        losses.build_mae_loss(p, t, "huber")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        losses.mae_l2_loss(p, t, True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        losses.mae_recon_loss(p, t, "cosine", False)
 
 
 def test_fedavg_known_answer(host):
@@ -158,3 +160,58 @@ def test_noise_identity_for_nonpositive_sigma(host):
     assert add_gaussian_noise(z, 0.0) is z and add_gaussian_noise(z, -1.0) is z
     with pytest.raises(RuntimeError):
         add_gaussian_noise(z, 0.1)   # CPU tensor: there is no CPU path
+
+
+# ---- round 2: the reference's literal defaults (checkpointing + drop-path) and the stack-2 mask/gather logic -----------
+@pytest.fixture(scope="module")
+def defaults(golden_dir):
+    return torch.load(os.path.join(golden_dir, "stack1_defaults.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def stack2(golden_dir):
+    return torch.load(os.path.join(golden_dir, "stack2_mae.pt"), weights_only=False)
+
+
+def test_restatement_with_recorded_drop_path_masks_matches_reference_defaults(defaults):
+    """Live reference with use_checkpoint=True, drop_path_rate=0.1 (its defaults) vs the oracle fed the recorded keep masks:
+    checkpointing must not change pred / loss / gradients, drop-path enters only through the masks."""
+    d = defaults
+    model = build_ours(d["config"], seed=d["seed"])
+    sd0 = R.perturb_state_dict(model.state_dict(), seed=d["perturb_seed"])
+    sd = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and "running" not in k else v) for k, v in sd0.items()}
+    m = d["config"]["model"]
+    assert sorted(d["drop_masks"]) == ["stages.0.1", "stages.1.1", "stages.1.2"] + [f"stages.2.{j}" for j in range(1, 7)]
+    assert any(float(t.min()) == 0.0 for v in d["drop_masks"].values() for t in v[1:]), "the golden must actually drop a path"
+    pred = R.tiny_video_mae_forward(sd, d["clip"], d["mask"], m["decoder_depth"], m["decoder_num_heads"], drop_masks=d["drop_masks"])
+    assert torch.allclose(pred, d["pred"], rtol=1e-4, atol=3e-5)
+    loss = R.masked_mse(pred, d["clip"], d["mask"], 1, 8, True)
+    assert float(loss) == pytest.approx(float(d["loss"]), rel=1e-5)
+    loss.backward()
+    for k, gref in d["grads"].items():
+        g = sd[k].grad
+        assert g is not None, k
+        assert torch.allclose(g, gref, rtol=2e-3, atol=1e-6 + 2e-4 * float(gref.abs().max())), k
+    # SURVEY §5: BatchNorm layers inside checkpointed stages count (and update) twice per step, the un-checkpointed stem once
+    nbt = d["num_batches_tracked"]
+    assert nbt["encoder.patch_embed.patch_embed.0.bn.num_batches_tracked"] == 1
+    assert nbt["encoder.stages.0.0.conv.0.bn.num_batches_tracked"] == 2
+    assert nbt["encoder.stages.2.0.conv.5.bn.num_batches_tracked"] == 2
+    assert nbt["encoder.stages.3.0.conv.0.bn.num_batches_tracked"] == 0      # stage 3 is not executed by the MAE
+
+
+def test_stack2_restatement_matches_reference_mask_and_gather(stack2):
+    s = stack2
+    dec = s["decoder"]
+    tok = s["tokens"].reshape(s["B"], s["T"] * s["P"], s["D"])
+    for mode, case in s["cases"].items():
+        sd = {k: v.clone().requires_grad_(True) for k, v in s["state"].items()}
+        scale = sd["encoder.scale"]
+        pred, target = R.tinyvit_mae_forward(sd, tok * scale, case["token_mask"], dec["depth"], dec["num_heads"])
+        assert pred.shape == case["pred"].shape and torch.equal(target, case["target"]), mode       # gather rows bit-exact
+        assert torch.allclose(pred, case["pred"], rtol=1e-4, atol=2e-5), mode
+        loss = R.mae_l2_loss(pred, target, True)
+        assert float(loss) == pytest.approx(float(case["loss"]), rel=1e-5)
+        loss.backward()
+        for k, gref in case["grads"].items():
+            assert torch.allclose(sd[k].grad, gref, rtol=2e-3, atol=1e-7 + 2e-4 * float(gref.abs().max())), (mode, k)
