@@ -86,6 +86,25 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (its NUMA node), so that the pinned staging buffers are
+    first-touched there and the H2D copies of 8 ranks do not all cross one socket. Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        maskw = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(maskw) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed) or sorted(allowed)
+        os.sched_setaffinity(0, cpus)
+        return {"cpus": f"{cpus[0]}-{cpus[-1]}", "n": len(cpus), "all": sorted(allowed)}
+    except Exception as exc:   # containers without NVML / cpusets: leave the affinity alone
+        return {"cpus": None, "error": type(exc).__name__}
+
+
 def make_inputs(batch, cfg, seed):
     from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
 
@@ -106,6 +125,7 @@ def cpu_reference_step_factory(cfg, batch, threads):
     from ssl_vit_video_analytics_b200.models import VideoMAEViT
 
     torch.set_num_threads(threads)
+    R.USE_SDPA = True   # the reference's own attention call (tiny_vit.py:103): the fastest CPU path PyTorch has
     torch.manual_seed(0)
     model = VideoMAEViT(cfg)  # parameter container only (constructed on CPU; its forward is never called here)
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
@@ -122,6 +142,86 @@ def cpu_reference_step_factory(cfg, batch, threads):
         return float(loss.detach())
 
     return step
+
+
+def time_cpu_reference_model_a(steps, warmup, threads):
+    """BASELINE.md §3 row "CPU-ref": the reference's step body (src/train_ssl_mae.py:71-89) on TinyVideoMAE at C1 (B=2, T=8, 112x112,
+    tube mask 0.9), fp32, through the oracle restatement (pinned against the live reference by tests/golden), + AdamW(5e-4, 0.05)."""
+    from oracle import restatement as R
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+    from ssl_vit_video_analytics_b200.models import TinyVideoMAE, tiny_vit_21m_variant
+
+    torch.set_num_threads(threads)
+    R.USE_SDPA = True
+    cfg = {"dataset": {"clip_len": 8, "image_size": 112}, "model": {"decoder_embed_dim": 384, "decoder_depth": 4, "decoder_num_heads": 6, "decoder_dropout": 0.0}}
+    torch.manual_seed(0)
+    model = TinyVideoMAE(tiny_vit_21m_variant(img_size=112, use_checkpoint=False, drop_path_rate=0.0), cfg)   # parameter container only
+    sd0 = R.perturb_state_dict(model.state_dict(), seed=1234)
+    sd = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and "running" not in k else v) for k, v in sd0.items()}
+    params = [v for k, v in sd.items() if torch.is_tensor(v) and v.requires_grad and not k.startswith("encoder.stages.3.")]
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.05)
+    g = torch.Generator().manual_seed(0)
+    clip = torch.randn(2, 3, 8, 112, 112, generator=g)
+
+    def step():
+        mask = get_tube_mask(2, 8, 196, 0.9)
+        opt.zero_grad(set_to_none=True)
+        pred = R.tiny_video_mae_forward(sd, clip, mask, 4, 6)
+        loss = R.masked_mse(pred, clip, mask, 1, 8, True)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return 2 * steps / dt, dt / steps * 1e3
+
+
+def time_gpu_eager(cfg, batch, steps, warmup, dev):
+    """BASELINE.md §3 row "GPU-eager-ref": the SAME model-B step written in plain PyTorch (the oracle restatement: nn.functional
+    conv3d / linear / layer_norm / scaled_dot_product_attention / gelu, i.e. cuDNN + cuBLAS + flash-SDPA), bf16 autocast, same batch,
+    torch's fused AdamW, on the same B200. None of our kernels run here. This is the library baseline our kernels have to beat."""
+    from oracle import restatement as R
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+
+    R.USE_SDPA = True
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg)   # parameter container only
+    sd = {k: v.detach().to(dev).requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-4, weight_decay=0.05, fused=True)
+    clip, mask, _ = make_inputs(batch, cfg, seed=0)
+    clip, mask = clip.to(dev), mask.to(dev)
+    m = cfg["model"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = R.videomae_vit_forward(sd, clip, mask, m["depth"], m["num_heads"], m["decoder_depth"], m["decoder_num_heads"], tuple(m["tubelet"]))
+        loss = R.masked_mse(pred, clip, mask, m["tubelet"][0], m["tubelet"][1], True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "final_loss": float(loss.detach()),
+           "what": f"oracle/restatement.py videomae_vit_forward on cuda, bf16 autocast, F.scaled_dot_product_attention + cuBLAS + cuDNN, "
+                   f"torch.optim.AdamW(fused=True), batch {batch}, {steps} steps after {warmup} warm-up; embeds all tubelets then gathers (eager has no fused gather)"}
+    del sd, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 def time_cpu_reference(cfg, batch, steps, warmup, threads):
@@ -175,6 +275,7 @@ def run_ours(args, cfg):
         raise RuntimeError("bench.py (our arm) needs a B200: the sm_100a kernels have no fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: first touch then lands on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     use_graph = args.graph != "off"
@@ -217,9 +318,13 @@ def run_ours(args, cfg):
         ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())
         clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
         mask_d, vis_d = mask_h.to(dev), vis_h.to(dev)
+        # every input buffer owns its (static) mask tensors: the e2e loop draws a fresh tube mask per step on the host, like
+        # train_ssl_mae.py:71, and uploads it next to the clip
+        masks_of = {}
 
         def loss_fn(clip):
-            return model.training_loss(clip, mask_d, vis_d)
+            md, vd = masks_of.get(clip.data_ptr(), (mask_d, vis_d))
+            return model.training_loss(clip, md, vd)
     if args.optimizer == "fused":
         opt = FusedAdamW([p for p in model.parameters()], lr=5e-4, weight_decay=0.05)   # row a18: one launch, device-side hyper-parameters
     else:   # A/B: PyTorch's multi-tensor AdamW
@@ -281,6 +386,15 @@ def run_ours(args, cfg):
     barrier()
     copy_stream = torch.cuda.Stream(device=dev)
     bufs = [torch.empty_like(clip_d), torch.empty_like(clip_d)]
+    refresh_masks = args.workload == "vit_s"
+    if refresh_masks:
+        from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
+
+        mask_pinned = [mask_h.clone().pin_memory() for _ in range(2)]
+        vis_pinned = [vis_h.clone().pin_memory() for _ in range(2)]
+        for b in bufs:
+            masks_of[b.data_ptr()] = (mask_d.clone(), vis_d.clone())
+        Tp_, Lp_ = mask_h.shape[1], mask_h.shape[2]
     if use_graph:
         bufs[0].copy_(clip_d)
         bufs[1].copy_(clip_d)
@@ -322,10 +436,23 @@ def run_ours(args, cfg):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    mask_bytes = 0
+
     def issue_copy(i):
+        nonlocal mask_bytes
+        if refresh_masks:   # a fresh tube mask per step, drawn on the host as the reference does (train_ssl_mae.py:71)
+            ready[i % 2].synchronize()        # the pinned mask staging of this slot is free once its previous H2D copy (two steps ago) is done
+            mh = get_tube_mask(B, Tp_, Lp_, cfg["ssl"]["mask_ratio"])
+            mask_pinned[i % 2].copy_(mh)
+            vis_pinned[i % 2].copy_(visible_indices(mh))
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % 2])
             bufs[i % 2].copy_(clip_pinned[i % 2], non_blocking=True)
+            if refresh_masks:
+                md, vd = masks_of[bufs[i % 2].data_ptr()]
+                md.copy_(mask_pinned[i % 2], non_blocking=True)
+                vd.copy_(vis_pinned[i % 2], non_blocking=True)
+                mask_bytes = mask_pinned[0].numel() * mask_pinned[0].element_size() + vis_pinned[0].numel() * vis_pinned[0].element_size()
             ready[i % 2].record(copy_stream)
 
     loss_hosts = [torch.zeros((), dtype=torch.float32).pin_memory(), torch.zeros((), dtype=torch.float32).pin_memory()]
@@ -470,13 +597,30 @@ def run_ours(args, cfg):
                    "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": ("optim.FusedAdamW (vmae_adamw_multi)" if args.optimizer == "fused" else "torch.optim.AdamW(fused)"),
                    "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else ("after backward, between two graphs" if use_graph else "bucketed, overlapped with backward")), "final_loss": final_loss},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4, "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4 + mask_bytes, "d2h_bytes_per_step": 4, "numa_binding": {k: v for k, v in numa.items() if k != "all"},
+                "mask": ("fresh tube mask drawn on the host and uploaded every step" if refresh_masks else "static"),
                 "ms_per_step": e2e_ms / args.steps, "h2d_ms_alone": h2d_ms_alone, "uint8_frames_input": e2e_u8, "note": "pinned fp32 clip batch copied H2D every step (double-buffered on a copy stream); the loss of every step is copied D2H to pinned memory and read by the host one step later, inside the timed region"},
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if world == 1 and not args.no_gpu_eager and args.workload == "vit_s":
+        try:
+            torch.cuda.empty_cache()
+            ge = time_gpu_eager(cfg, B, max(3, min(args.steps, 10)), 3, dev)
+            ge["ours_over_eager"] = value / ge["value"]
+            line["gpu_eager_baseline"] = ge
+        except Exception as ex:
+            line["gpu_eager_baseline"] = {"value": None, "unit": UNIT, "what": f"failed: {ex!r}"}
     if world == 1 and not args.no_cpu_baseline and args.workload == "vit_s":
-        threads = os.cpu_count() or 1
+        if numa.get("all"):
+            os.sched_setaffinity(0, numa["all"])   # the CPU legs use every host core again
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        try:
+            va, msa = time_cpu_reference_model_a(3, 1, threads)
+            line["cpu_baseline_model_a"] = {"value": va, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": msa,
+                                            "sample": "oracle restatement of the reference step (train_ssl_mae.py:71-89) on TinyVideoMAE at C1: B=2, T=8, 112x112, mask 0.9, fp32, AdamW; 3 steps after 1 warm-up"}
+        except Exception as ex:
+            line["cpu_baseline_model_a"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {ex!r}"}
         try:
             v, ms = time_cpu_reference(cfg, 2, 3, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -496,6 +640,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the plain-PyTorch (cuBLAS/cuDNN/SDPA) comparator leg")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused = optim.FusedAdamW (default); torch = torch.optim.AdamW(fused=True), for A/B runs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step from CUDA graphs (default on; under torchrun the NCCL allreduce runs between two graphs)")

@@ -146,11 +146,16 @@ def _mbconv(sd: SD, p: str, x: Tensor, stride: int, bn_train: bool, drop=None) -
     return x + _drop_path(h, drop) if (stride == 1 and cin == h.shape[1]) else h
 
 
+USE_SDPA = False   # True: F.scaled_dot_product_attention, the call the reference itself makes (tiny_vit.py:103); same arithmetic
+
+
 def attention_core(qkv: Tensor, num_heads: int) -> Tensor:
     """tiny_vit.py:97-104 / the MHA core of nn.TransformerEncoderLayer: qkv [B, L, 3*H*hd] (q|k|v, head, dim)."""
     B, L, W3 = qkv.shape
     hd = W3 // (3 * num_heads)
     q, k, v = qkv.reshape(B, L, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    if USE_SDPA:
+        return F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, num_heads * hd)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
     return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, L, num_heads * hd)
 

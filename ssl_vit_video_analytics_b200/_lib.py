@@ -9,7 +9,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libvmae_sm100a.so"
+LIB_PATH = Path(os.environ.get("VMAE_LIB_OVERRIDE") or (_PKG / "lib" / "libvmae_sm100a.so"))   # override: developer A/B builds only
 
 DTYPE_BF16, DTYPE_F32 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1

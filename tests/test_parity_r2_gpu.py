@@ -129,7 +129,7 @@ def test_tinyvideomae_reference_defaults_checkpoint_and_drop_path(golden_dir):
     for k, n in d["num_batches_tracked"].items():
         assert int(sd[k]) == n, (k, int(sd[k]), n)
     for k, (s, a) in d["running_checksums"].items():
-        assert float(sd[k].double().abs().sum()) == pytest.approx(a, rel=2e-2, abs=1e-3), k
+        assert float(sd[k].double().abs().sum()) == pytest.approx(a, rel=5e-2, abs=1e-3), k
     # checkpointing must not change the result: same masks, use_checkpoint=False
     model2 = _build_defaults_model(d, use_checkpoint=False)
     pred2, loss2, grads2 = _run_defaults(model2, d)
