@@ -356,14 +356,19 @@ def run_ours(args, cfg):
         ddp.finish_gradient_sync()
         return loss
 
-    graphed = GraphedTrainStep(eager_step if world == 1 else fwd_bwd)
-    opt_graph = torch.cuda.CUDAGraph() if (use_graph and world > 1) else None
+    # --allreduce captured (default for N > 1): the whole step is ONE graph also under torchrun — the bucket allreduces are
+    # launched by the gradient hooks on the communication stream, which forks from the capture stream at "bucket complete" and
+    # joins before AdamW, so NCCL runs underneath the rest of backward inside the replayed graph.
+    # --allreduce between: graph 1 (forward+backward), eager allreduces, graph 2 (AdamW): the round-1 arrangement, exposed collective.
+    ar_captured = world > 1 and args.allreduce == "captured"
+    graphed = GraphedTrainStep(eager_step if (world == 1 or ar_captured) else fwd_bwd)
+    opt_graph = torch.cuda.CUDAGraph() if (use_graph and world > 1 and not ar_captured) else None
 
     def step(clip):
         if not use_graph:
             return eager_step(clip)
         loss = graphed.replay(clip)
-        if world > 1:
+        if opt_graph is not None:
             ddp.allreduce_now()
             opt_graph.replay()
         return loss
@@ -398,7 +403,7 @@ def run_ours(args, cfg):
     if use_graph:
         bufs[0].copy_(clip_d)
         bufs[1].copy_(clip_d)
-        ddp.defer_comm = world > 1
+        ddp.defer_comm = world > 1 and not ar_captured
         try:
             for t in (clip_d, bufs[0], bufs[1]):
                 graphed.capture(t)
@@ -561,9 +566,21 @@ def run_ours(args, cfg):
         v["launches"] /= 2.0
         v["work"] /= 2.0
 
+    def leave():
+        """Multi-rank exit. With NCCL kernels captured in CUDA graphs, destroying the communicator while the graphs are alive hangs
+        (observed: rank 1 stuck in destroy_process_group until torchrun's timeout), so: everybody syncs, the graphs are dropped,
+        and the process leaves without the NCCL teardown (the OS reclaims it)."""
+        if world == 1:
+            return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
     peaks = load_peaks()
     ms_step = ms_total / args.steps
@@ -595,7 +612,7 @@ def run_ours(args, cfg):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_policy": "inputs larger than L2 (clip batch of hundreds of MB, >10 GB activations per step)", "optimizer": ("optim.FusedAdamW (vmae_adamw_multi)" if args.optimizer == "fused" else "torch.optim.AdamW(fused)"),
-                   "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else ("after backward, between two graphs" if use_graph else "bucketed, overlapped with backward")), "final_loss": final_loss},
+                   "cuda_graph": use_graph, "grad_allreduce": ("none" if world == 1 else (("bucketed NCCL allreduce on a forked stream inside the captured step, overlapped with backward" if ar_captured else "after backward, between two graphs") if use_graph else "bucketed, hook-driven, overlapped with backward (eager launches)")), "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_h.numel() * 4 + mask_bytes, "d2h_bytes_per_step": 4, "numa_binding": {k: v for k, v in numa.items() if k != "all"},
                 "mask": ("fresh tube mask drawn on the host and uploaded every step" if refresh_masks else "static"),
@@ -628,8 +645,118 @@ def run_ours(args, cfg):
         except Exception as ex:  # the baseline must never take the measured line down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {ex!r}"}
     print(json.dumps(line), flush=True)
+    leave()
+
+
+# ======================================================================================================================
+# BASELINE config 5: FedAvg simulation, 5 clients mapped across the GPUs of one box (src/federated/fed_loop.py:65-147)
+# ======================================================================================================================
+def run_fedavg(args, cfg):
+    """One round = every client runs `--local-steps` MAE pretraining steps on its own GPU from the current global model, then the
+    models are aggregated with the weighted allreduce `federated.fed_loop.fedavg_allreduce` (pre-scale by w_k / sum w, NCCL
+    allreduce(sum); clients = ranks 0..4, weights = synthetic dataset sizes as in run_federated.py:288; further ranks are idle and
+    contribute weight 0). The reference does this sequentially on one device and aggregates on the CPU (fed_loop.py:109-119)."""
+    import torch.distributed as dist
+
+    from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.federated.fed_loop import fedavg_allreduce
+    from ssl_vit_video_analytics_b200.graph_step import GraphedTrainStep, use_side_stream
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+    from ssl_vit_video_analytics_b200.optim import FusedAdamW
+    from ssl_vit_video_analytics_b200.parallel import GradientBucketer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.destroy_process_group()
+        dist.init_process_group("nccl", device_id=dev)
+    use_side_stream(dev)
+    sizes = [1907, 1893, 1921, 1880, 1936]                       # SURVEY.md 8(d): client dataset sizes
+    n_clients = min(len(sizes), world)
+    is_client = rank < n_clients
+    weight = float(sizes[rank]) if is_client else 0.0
+    B = PER_GPU_BATCH if args.batch is None else args.batch
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg).to(dev).train()
+    ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())    # broadcasts rank 0's weights = the initial global model
+    ddp.world = 1                                                # clients train independently: no gradient exchange inside a round
+    opt = FusedAdamW(list(model.parameters()), lr=5e-4, weight_decay=0.05)
+    clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
+    clip_d, mask_d, vis_d = clip_h.to(dev), mask_h.to(dev), vis_h.to(dev)
+
+    def local_step(clip):
+        ddp.zero_grad()
+        loss = model.training_loss(clip, mask_d, vis_d)
+        loss.backward()
+        ddp.finish_gradient_sync()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        local_step(clip_d)
+    graphed = GraphedTrainStep(local_step)
+    graphed.capture(clip_d)
+
+    def one_round():
+        if is_client:
+            for _ in range(args.local_steps):
+                graphed.replay(clip_d)
+        fedavg_allreduce(model, weight)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        one_round()
+    barrier()
+    ops.reset_launch_count()
+    e0, e1, ea = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rounds = max(1, args.steps // max(1, args.local_steps))
+    agg_ms = 0.0
+    e0.record()
+    for _ in range(rounds):
+        if is_client:
+            for _ in range(args.local_steps):
+                graphed.replay(clip_d)
+        ea.record()
+        fedavg_allreduce(model, weight)
+        e1.record()
+        e1.synchronize()
+        agg_ms += ea.elapsed_time(e1)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms, agg_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, agg_ms = float(t[0]), float(t[1])
+    check = torch.cat([p.detach().flatten()[:64].double() for p in list(model.parameters())[:4]]).sum().reshape(1)
+    lo, hi = check.clone(), check.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        clips = n_clients * B * args.local_steps * rounds
+        n_floats = sum(v.numel() for v in model.state_dict().values() if torch.is_floating_point(v))
+        line = {"metric": "fedavg_round_clips_per_sec", "value": clips / (total_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": rounds * args.local_steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / (rounds * args.local_steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "FedAvg simulation (BASELINE configs[4]): 5 clients on the first 5 GPUs, local ViT-S VideoMAE pretraining steps + weighted-allreduce aggregation per round",
+                           "clients": n_clients, "client_weights": sizes[:n_clients], "local_steps": args.local_steps, "rounds": rounds, "per_gpu_batch": B,
+                           "idle_ranks": max(0, world - n_clients)},
+                "fedavg": {"round_ms": total_ms / rounds, "aggregate_ms": agg_ms / rounds, "state_floats": n_floats,
+                           "aggregate_gbs_per_gpu": 2 * 4 * n_floats / (agg_ms / rounds / 1e3) / 1e9 if agg_ms > 0 else None,
+                           "replicas_identical_after_round": bool(float(lo) == float(hi))},
+                "gpu_launches": ops.launch_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 def main():
@@ -644,14 +771,21 @@ def main():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused = optim.FusedAdamW (default); torch = torch.optim.AdamW(fused=True), for A/B runs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step from CUDA graphs (default on; under torchrun the NCCL allreduce runs between two graphs)")
-    ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit"],
-                    help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes")
+    ap.add_argument("--allreduce", default="captured", choices=["captured", "between"],
+                    help="N > 1 with graphs: captured = NCCL bucket allreduces inside the one captured step, overlapped with backward (default); "
+                         "between = eager allreduces between a forward+backward graph and an AdamW graph")
+    ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit", "fedavg"],
+                    help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes; "
+                         "fedavg = BASELINE config 5 (5 clients across the GPUs, local steps + weighted-allreduce aggregation)")
+    ap.add_argument("--local-steps", type=int, default=4, help="fedavg: local training steps per client and round")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from ssl_vit_video_analytics_b200.models.videomae_vit import DEFAULT_CONFIG
 
     if args.impl == "reference":
         run_reference(args, DEFAULT_CONFIG)
+    elif args.workload == "fedavg":
+        run_fedavg(args, DEFAULT_CONFIG)
     else:
         run_ours(args, DEFAULT_CONFIG)
 

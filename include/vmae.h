@@ -56,6 +56,14 @@ int vmae_gemm_bf16(const void* A, long long lda, int a_major, const void* B, lon
                    long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out, long long ld_out,
                    int out_dtype, int accumulate, int act, int k_splits, void* stream);
 
+/* Forward GEMM with the feature perturbation z' = z + N(0, sigma^2 I) of privacy/feature_noise.py:4-7 (call site run_privacy.py:299)
+ * fused into its epilogue: out[M,N] (bf16) = A[M,K] B[N,K]^T + bias + sigma * eps. eps comes from Philox4x32-10 keyed by
+ * (seed, offset + (m*N + n) / 4), lane (m*N + n) % 4 — the same stream vmae_add_gaussian_noise draws for the flattened [M,N]
+ * tensor. eps_out (optional, fp32 dense [M,N]) receives the normals, so parity is exact given eps. */
+int vmae_gemm_bf16_noise(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const float* bias,
+                         void* out, long long ld_out, float sigma, unsigned long long seed, unsigned long long offset,
+                         float* eps_out, void* stream);
+
 /* Weight + bias gradient of y = x W^T + b in one launch (split-K, fp32 accumulation into existing buffers):
  *   dw[n_out, k_in] += dy[tokens, n_out]^T x[tokens, k_in];   dbias[n_out] += column sums of dy (optional, may be NULL)
  * The bias gradient costs one extra N=16 UMMA per K step against an all-ones tile (no second pass over dy). */
@@ -155,6 +163,19 @@ int vmae_decoder_input_bwd(const float* dx_dec, const int* vis_idx, const unsign
 int vmae_pos_rows_bwd(const float* dx, const int* vis_idx, float* dtpos, float* dspos, int B, int Tp, int n_vis, int D,
                       void* stream);
 
+/* ---- K6 as ONE kernel: tubelet embedding of the visible tubes = implicit GEMM over the clip (north_star bullet 1) ----------------
+ * out[m,:] (fp32 [B*(T/pt)*n_vis, E]) = W patch(m) + bias + temporal_pos[tp(m),:] + spatial_pos[l(m),:], rows in gathered order
+ * (clip, temporal slot, i-th visible patch; l = vis_idx[b,i]). weight: bf16 [E, 3*pt*ps*ps] = the Conv3d weight [E,3,pt,ps,ps]
+ * flattened (K order c, dt, py, px). The A operand is gathered by 5-D TMA boxes straight from clip fp32 [B,3,T,H,W]; no patch
+ * matrix is materialised. ps must be 16, E a multiple of 64 (<= 384); other geometries return VMAE_ERR_UNSUPPORTED.
+ * wgrad: dw[E, 3*pt*ps*ps] (fp32, ACCUMULATED) += dy^T patches, dy bf16 [rows, E]; E and K multiples of 128.
+ * (bias gradient = vmae_colsum_accum(dy), positional gradients = vmae_pos_rows_bwd(dy).) */
+int vmae_tubelet_embed_fwd(const float* clip, const int* vis_idx, const void* weight_bf16, const float* bias,
+                           const float* temporal_pos, const float* spatial_pos, float* out, int B, int T, int H, int W, int pt,
+                           int ps, int n_vis, int E, void* stream);
+int vmae_tubelet_embed_wgrad(const float* clip, const int* vis_idx, const void* dy_bf16, float* dw, int B, int T, int H, int W,
+                             int pt, int ps, int n_vis, int E, void* stream);
+
 /* ---- K7: TinyViT convolution kit on channels-last bf16 feature maps (rows = pixels), tiny_vit.py:12-72 ---------------
  * Train-mode BatchNorm2d (batch statistics over the M = N*H*W rows, biased variance for normalisation, running statistics
  * updated with `momentum` and the unbiased variance, as nn.BatchNorm2d) with optional fused exact GELU and residual add:
@@ -233,6 +254,12 @@ int vmae_scatter_rows(const void* src, int dtype, const int* idx, void* dst, lon
  * bin i covers [floor(i*H/s), ceil((i+1)*H/s)). bwd: dx bf16 [N,H,W,C] from dout fp32 [N, s*s, C]. */
 int vmae_adaptive_avgpool_fwd(const void* x, float* out, int N, int H, int W, int C, int s, void* stream);
 int vmae_adaptive_avgpool_bwd(const float* dout, void* dx, int N, int H, int W, int C, int s, void* stream);
+
+/* Video embedding + feature noise (train_finetune.py:19-40 pooled feature; feature_noise.py:4-7 at run_privacy.py:299):
+ * out[b,:] (fp32 [B,D]) = mean over the n token rows of x[b] (bf16 [B,n,D]) + sigma * eps; Philox stream of the flattened [B,D]
+ * output (as vmae_add_gaussian_noise); eps_out optional (fp32 [B,D]); sigma == 0: plain mean. D % 64 == 0. */
+int vmae_meanpool_noise(const void* x, float* out, float* eps_out, int B, int n, int D, float sigma, unsigned long long seed,
+                        unsigned long long offset, void* stream);
 
 /* ---- K10: fused softmax cross-entropy of the finetune head (train_finetune.py:86-107, nn.CrossEntropyLoss, mean reduction) ----
  * fwd: logits bf16|fp32 [rows, C], labels int64 [rows] -> lse fp32 [rows] (saved), row_loss fp32 [rows], loss fp32 scalar = mean.

@@ -296,6 +296,28 @@ def videomae_vit_forward(sd: SD, clip: Tensor, mask: Tensor, depth: int, heads: 
     return _decoder(sd, x_dec, decoder_depth, decoder_heads)
 
 
+def videomae_vit_classifier_forward(sd: SD, clip: Tensor, depth: int, heads: int, tubelet=(2, 16, 16), sigma: float = 0.0, eps: Tensor = None):
+    """BASELINE config 4 (composition, no reference implementation): the ViT-S tubelet encoder above on ALL tokens -> LayerNorm ->
+    mean over tokens (the GAP + temporal mean of train_finetune.py:19-40) -> z + sigma * eps (feature_noise.py:4-7, eps supplied)
+    -> nn.Linear head (heads.py:6-21). Keys: backbone.{patch_embed,enc_*_pos_embed,blocks,norm}.*, classifier.*. -> (logits, z)."""
+    B = clip.shape[0]
+    p = "backbone."
+    tok = F.conv3d(clip, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=tubelet)
+    E = tok.shape[1]
+    tok = tok.flatten(3).permute(0, 2, 3, 1) + (sd[p + "enc_temporal_pos_embed"] + sd[p + "enc_spatial_pos_embed"])
+    x = tok.reshape(B, -1, E)
+    for i in range(depth):
+        q = f"{p}blocks.{i}"
+        x = transformer_block(x, sd[q + ".norm1.weight"], sd[q + ".norm1.bias"], sd[q + ".attn.qkv.weight"], sd[q + ".attn.qkv.bias"],
+                              sd[q + ".attn.proj.weight"], sd[q + ".attn.proj.bias"], sd[q + ".norm2.weight"], sd[q + ".norm2.bias"],
+                              sd[q + ".mlp.fc1.weight"], sd[q + ".mlp.fc1.bias"], sd[q + ".mlp.fc2.weight"], sd[q + ".mlp.fc2.bias"], heads)
+    x = F.layer_norm(x, (E,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    z = x.mean(dim=1)
+    if sigma > 0:
+        z = add_gaussian_noise(z, sigma, eps)
+    return F.linear(z, sd["classifier.weight"], sd["classifier.bias"]), z
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # feature noise, FedAvg
 # ----------------------------------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ SIGNATURES = {
     "vmae_abi_version": [],
     "vmae_device_sm_count": [],
     "vmae_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
+    "vmae_gemm_bf16_noise": [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _ll, _f, _ull, _ull, _p, _p],
     "vmae_linear_wgrad": [_p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _i, _p],
     "vmae_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
     "vmae_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _ull, _p],
@@ -40,6 +41,8 @@ SIGNATURES = {
     "vmae_masked_mse_bwd": [_p, _p, _p, _p, _ll, _p],
     "vmae_mask_to_indices": [_p, _p, _i, _i, _i, _p],
     "vmae_gather_tubelets": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vmae_tubelet_embed_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vmae_tubelet_embed_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "vmae_decoder_input_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vmae_decoder_input_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vmae_pos_rows_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -69,6 +72,7 @@ SIGNATURES = {
     "vmae_scatter_rows": [_p, _i, _p, _p, _ll, _ll, _i, _p],
     "vmae_adaptive_avgpool_fwd": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vmae_adaptive_avgpool_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "vmae_meanpool_noise": [_p, _p, _p, _i, _i, _i, _f, _ull, _ull, _p],
     "vmae_softmax_ce_fwd": [_p, _i, _p, _p, _p, _p, _ll, _i, _p],
     "vmae_softmax_ce_bwd": [_p, _i, _p, _p, _p, _p, _ll, _i, _p],
 }

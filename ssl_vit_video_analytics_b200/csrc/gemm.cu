@@ -22,6 +22,7 @@
 // global traffic is full-line bulk copies and edge tiles are clipped by the TMA unit.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "philox.cuh"
 #include "../../include/vmae.h"
 
 namespace vmae {
@@ -40,6 +41,8 @@ enum : int {
   EPI_F32 = 3,         // out f32  = acc (+bias)
   EPI_F32_RESID = 4,   // out f32  = acc (+bias) + residual
   EPI_F32_ACCUM = 5,   // out f32 += acc            (TMA reduce-add; split-K)
+  EPI_BF16_NOISE = 6,  // out bf16 = acc (+bias) + sigma * N(0,1)  (privacy/feature_noise.py:4-7 fused into the producing GEMM; Philox
+                       //            keyed on (seed, offset + flattened element index / 4): the stream of the stand-alone kernel)
 };
 
 template <int EPI>
@@ -58,6 +61,10 @@ struct GemmParams {
   int k_splits;
   const float* bias;  // [N] fp32 or null
   float* bias_grad;   // EPI_F32_ACCUM only: [M] fp32, += sum over the contraction dimension of A (ones-column UMMA)
+  // EPI_BF16_NOISE only
+  float sigma;
+  unsigned long long seed, offset;
+  float* eps_out;     // optional fp32 [M, N] (dense): the unit normals that were drawn (exact-parity tests)
 };
 
 template <int BLOCK_N, int EPI>
@@ -359,8 +366,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
+        if (EPI == EPI_BF16_NOISE) {
+          // z' = z + sigma * eps: this thread owns 32 consecutive columns of row gm + r, i.e. 8 Philox counters of the flattened
+          // [M, N] output (N % 8 == 0 and gn % 32 == 0, so the 4-element groups never straddle a row)
+          const long long row = gm + r;
+          const long long base = row * p.N + gn;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 e = philox_normal4(p.seed, p.offset + static_cast<unsigned long long>((base + 4 * j) >> 2));
+            v[4 * j] = __fmaf_rn(p.sigma, e.x, v[4 * j]);
+            v[4 * j + 1] = __fmaf_rn(p.sigma, e.y, v[4 * j + 1]);
+            v[4 * j + 2] = __fmaf_rn(p.sigma, e.z, v[4 * j + 2]);
+            v[4 * j + 3] = __fmaf_rn(p.sigma, e.w, v[4 * j + 3]);
+            if (p.eps_out != nullptr && row < p.M && gn + 4 * j < p.N) *reinterpret_cast<float4*>(p.eps_out + base + 4 * j) = e;
+          }
+        }
         if (ET::HAS_IN) mbar_wait(in_bar(ew, b), (item >> 1) & 1u);
-        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_NOISE) {
           if (EPI == EPI_BF16_GELU) {
             // one evaluation of Phi(x) serves both gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x); the derivative is
             // what backward needs, so it is stored instead of the pre-activation (same bytes, and the dgrad epilogue
@@ -486,6 +508,7 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
     case EPI_BF16_DGELU: return dispatch_major<BLOCK_N, EPI_BF16_DGELU>(a_major, b_major, m, p, grid, stream);
     case EPI_F32: return dispatch_major<BLOCK_N, EPI_F32>(a_major, b_major, m, p, grid, stream);
     case EPI_F32_RESID: return dispatch_major<BLOCK_N, EPI_F32_RESID>(a_major, b_major, m, p, grid, stream);
+    case EPI_BF16_NOISE: return launch_gemm<BLOCK_N, 0, 0, EPI_BF16_NOISE>(m, p, grid, stream);   // forward layout only
     default:
       if constexpr (BLOCK_N <= 192) return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
       else return fail(VMAE_ERR_UNSUPPORTED, "accumulating GEMM with BLOCK_N=256 is not instantiated");
@@ -525,7 +548,9 @@ using namespace vmae;
 static int gemm_impl(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major,
                      int M, int N, int K, const float* bias, const float* residual, long long ld_res,
                      const void* aux_in, long long ld_aux_in, void* aux_out, long long ld_aux_out, void* out,
-                     long long ld_out, int out_dtype, int accumulate, int act, int k_splits, float* bias_grad, void* stream_) {
+                     long long ld_out, int out_dtype, int accumulate, int act, int k_splits, float* bias_grad, void* stream_,
+                     float noise_sigma = 0.f, unsigned long long noise_seed = 0, unsigned long long noise_offset = 0, float* eps_out = nullptr,
+                     bool noise = false) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VMAE_CHECK_ARG(A && B && out, "vmae_gemm_bf16: null operand");
   VMAE_CHECK_ARG(M > 0 && N > 0 && K > 0, "vmae_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -544,7 +569,12 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
 
   // epilogue selection (the fused combinations the training step uses; anything else is refused, never emulated)
   int epi;
-  if (accumulate) {
+  if (noise) {
+    VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && !accumulate && act == VMAE_ACT_NONE && !residual && !aux_in && !aux_out &&
+                       a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K,
+                   "vmae_gemm_bf16_noise: forward layout, bf16 output, bias only");
+    epi = EPI_BF16_NOISE;
+  } else if (accumulate) {
     epi = EPI_F32_ACCUM;
   } else if (act == VMAE_ACT_GELU) {
     VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && aux_out && !residual && !aux_in,
@@ -607,6 +637,10 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
   p.M = M; p.N = N; p.K = K; p.k_splits = k_splits;
   p.bias = bias;
   p.bias_grad = bias_grad;
+  p.sigma = noise_sigma;
+  p.seed = noise_seed;
+  p.offset = noise_offset;
+  p.eps_out = eps_out;
 
   const int m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (N + block_n - 1) / block_n;
@@ -632,4 +666,11 @@ extern "C" int vmae_linear_wgrad(const void* dy, long long ld_dy, const void* x,
   VMAE_CHECK_ARG(tokens > 0 && tokens < (1ll << 31), "vmae_linear_wgrad: bad token count %lld", tokens);
   return gemm_impl(dy, ld_dy, VMAE_MAJOR_MN, x, ld_x, VMAE_MAJOR_MN, n_out, k_in, (int)tokens, nullptr, nullptr, 0, nullptr, 0, nullptr, 0,
                    dw, ld_dw, VMAE_DTYPE_F32, 1, VMAE_ACT_NONE, k_splits, dbias, stream);
+}
+
+extern "C" int vmae_gemm_bf16_noise(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const float* bias, void* out,
+                                    long long ld_out, float sigma, unsigned long long seed, unsigned long long offset, float* eps_out, void* stream) {
+  VMAE_CHECK_ARG(sigma >= 0.f, "vmae_gemm_bf16_noise: sigma=%f must be >= 0", (double)sigma);
+  return gemm_impl(A, lda, VMAE_MAJOR_K, B, ldb, VMAE_MAJOR_K, M, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, out, ld_out, VMAE_DTYPE_BF16, 0,
+                   VMAE_ACT_NONE, 1, nullptr, stream, sigma, seed, offset, eps_out, true);
 }

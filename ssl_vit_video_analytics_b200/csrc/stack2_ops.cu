@@ -2,6 +2,7 @@
 // softmax cross-entropy of the finetune head (reference: src/train_finetune.py:86-107, nn.CrossEntropyLoss).
 // All HBM-bound: one warp per row, 128-bit accesses where the row pitch allows, shuffle reductions, no host sync.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace vmae {
 
@@ -223,9 +224,61 @@ __global__ void __launch_bounds__(256) adaptive_avgpool_bwd_kernel(const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Video embedding of the finetune / privacy path: z[b, :] = mean over the n token rows of clip b (GAP + temporal mean of
+// train_finetune.py:19-40 in token form), with the feature perturbation z' = z + sigma * N(0, 1) (feature_noise.py:4-7,
+// applied to exactly this pooled embedding at run_privacy.py:299) added in the same kernel. x bf16 [B, n, D] -> out fp32 [B, D].
+// Block = (clip, 64-channel slab): 8 lanes x 16 B across the slab, 32 row groups down the tokens, smem tree over the groups.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) meanpool_noise_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, float* __restrict__ eps_out,
+                                                             int n, int D, float sigma, unsigned long long seed, unsigned long long offset) {
+  __shared__ float red[32][65];
+  const int slabs = D / 64;
+  const int b = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const __nv_bfloat16* base = x + (static_cast<long long>(b) * n) * D + slab * 64 + cl * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = rg; t < n; t += 32) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * D));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      acc[2 * k] += f.x;
+      acc[2 * k + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rg][cl * 8 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) t += red[g][threadIdx.x];
+    float z = t / static_cast<float>(n);
+    const long long i = static_cast<long long>(b) * D + slab * 64 + threadIdx.x;
+    if (sigma > 0.f) {
+      const float4 e4 = philox_normal4(seed, offset + static_cast<unsigned long long>(i >> 2));
+      const int lane4 = static_cast<int>(i & 3);
+      const float e = lane4 == 0 ? e4.x : (lane4 == 1 ? e4.y : (lane4 == 2 ? e4.z : e4.w));
+      z = __fmaf_rn(sigma, e, z);
+      if (eps_out) eps_out[i] = e;
+    }
+    out[i] = z;
+  }
+}
+
 }  // namespace vmae
 
 using namespace vmae;
+
+extern "C" int vmae_meanpool_noise(const void* x, float* out, float* eps_out, int B, int n, int D, float sigma, unsigned long long seed,
+                                   unsigned long long offset, void* stream) {
+  VMAE_CHECK_ARG(x && out && B > 0 && n > 0 && D > 0 && D % 64 == 0 && sigma >= 0.f, "vmae_meanpool_noise: bad args (D %% 64 == 0, sigma >= 0)");
+  meanpool_noise_kernel<<<B * (D / 64), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, eps_out, n, D, sigma, seed, offset);
+  VMAE_LAUNCH_CHECK();
+  return VMAE_OK;
+}
 
 extern "C" int vmae_adaptive_avgpool_fwd(const void* x, float* out, int N, int H, int W, int C, int s, void* stream) {
   VMAE_CHECK_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && s > 0 && s <= H && s <= W, "vmae_adaptive_avgpool_fwd: bad args");

@@ -445,6 +445,71 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class LinearNoiseFn(torch.autograd.Function):
+    """y = x W^T + b + sigma * eps with eps ~ N(0, I) drawn in the GEMM epilogue (privacy/feature_noise.py:4-7 fused into the
+    producing Linear; Philox keyed on (seed, offset, element)). eps_out (optional fp32 [rows, N]) receives eps. The noise is an
+    additive constant: gradients are those of the Linear."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, sigma, seed, offset, eps_out):
+        _need_cuda(x, weight)
+        shp = x.shape
+        x2 = cast_bf16(x.reshape(-1, shp[-1]))
+        n_out = weight.shape[0]
+        wb = cast_weight(weight).reshape(n_out, -1)
+        bf = bias.float().contiguous() if bias is not None else None
+        M, K = x2.shape
+        y = torch.empty((M, n_out), device=x.device, dtype=BF16)
+        if eps_out is not None:
+            assert eps_out.dtype == F32 and eps_out.is_contiguous() and eps_out.numel() == M * n_out and eps_out.is_cuda
+        L.check(_run("gemm_fwd", 2.0 * M * n_out * K, lambda: L.load().vmae_gemm_bf16_noise(
+            _p(x2), x2.stride(0), _p(wb), wb.stride(0), M, n_out, K, _p(bf), _p(y), y.stride(0), float(sigma), int(seed) & 0xFFFFFFFFFFFFFFFF,
+            int(offset), _p(eps_out), _stream())), "vmae_gemm_bf16_noise")
+        _count()
+        ctx.save_for_backward(x2, wb)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = shp
+        ctx.in_dtype = x.dtype
+        ctx.w_shape = weight.shape
+        return y.reshape(*shp[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb = ctx.saved_tensors
+        dy2 = cast_bf16(dy.reshape(-1, dy.shape[-1]))
+        dx = linear_dgrad(dy2, wb) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] and ctx.has_bias and ctx.needs_input_grad[2]:
+            dw, db = linear_wgrad_bias(dy2, x2)
+        elif ctx.needs_input_grad[1]:
+            dw = linear_wgrad(dy2, x2)
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        if dw is not None:
+            dw = dw.reshape(ctx.w_shape)
+        if dx is not None:
+            dx = dx.reshape(ctx.in_shape)
+            if ctx.in_dtype == F32:
+                dx = cast_f32(dx)
+        return dx, dw, db, None, None, None, None
+
+
+_noise_offset = [0]
+
+
+def linear_with_feature_noise(x, weight, bias, sigma, seed=None, eps_out=None):
+    """nn.Linear followed by add_gaussian_noise(., sigma), as one kernel. sigma <= 0: the plain Linear (the reference returns z
+    itself). Successive calls advance a process-wide Philox offset so that they draw fresh normals under one seed."""
+    if sigma <= 0:
+        return LinearFn.apply(x, weight, bias, L.ACT_NONE)
+    if seed is None:
+        seed = torch.initial_seed()
+    rows = x.numel() // x.shape[-1]
+    off = _noise_offset[0]
+    _noise_offset[0] += (rows * weight.shape[0] + 3) // 4
+    return LinearNoiseFn.apply(x, weight, bias, float(sigma), int(seed), off, eps_out)
+
+
 def gelu_bwd(dy_bf16, pre_bf16):
     """dy * dact, where dact = gelu'(pre-activation) as saved by the GELU epilogue; used by the unfused LinearFn only."""
     out = torch.empty_like(dy_bf16)
@@ -784,6 +849,62 @@ class TubeletGatherFn(torch.autograd.Function):
         return None, None, dt.reshape(ctx.shapes[0]), ds.reshape(ctx.shapes[1]), None, None
 
 
+class TubeletEmbedFn(torch.autograd.Function):
+    """Tubelet embedding of the visible tubes as ONE implicit-GEMM kernel (K6): Conv3d(3, E, (pt,16,16), stride = kernel) evaluated
+    where the tube mask is 0 + bias + factorised positional rows, output fp32 [B*T'*n_vis, E] in gathered order. The clip is read
+    in place through 5-D TMA boxes (no patch matrix); backward re-gathers the same boxes for the weight gradient and reduces the
+    bias / positional gradients from dy. The clip gets no gradient (it is data)."""
+
+    @staticmethod
+    def forward(ctx, clip, vis_idx, weight, bias, tpos, spos, pt, ps):
+        _need_cuda(clip, vis_idx, weight)
+        B, Cc, T, H, W = clip.shape
+        assert Cc == 3 and clip.dtype == F32 and clip.is_contiguous() and vis_idx.dtype == torch.int32 and vis_idx.is_contiguous()
+        E = weight.shape[0]
+        n_vis = vis_idx.shape[1]
+        Tp = T // pt
+        wb = cast_weight(weight).reshape(E, -1)
+        rows = B * Tp * n_vis
+        out = torch.empty((rows, E), device=clip.device, dtype=F32)
+        tp2, sp2 = tpos.reshape(Tp, E).float().contiguous(), spos.reshape(-1, E).float().contiguous()
+        bf = bias.float().contiguous() if bias is not None else None
+        L.check(_run("gemm_fwd", 2.0 * rows * E * wb.shape[1], lambda: L.load().vmae_tubelet_embed_fwd(
+            _p(clip), _p(vis_idx), _p(wb), _p(bf), _p(tp2), _p(sp2), _p(out), B, T, H, W, pt, ps, n_vis, E, _stream())), "vmae_tubelet_embed_fwd")
+        _count()
+        ctx.save_for_backward(clip, vis_idx)
+        ctx.geom = (B, T, H, W, pt, ps, n_vis, E, Tp, sp2.shape[0])
+        ctx.shapes = (weight.shape, tpos.shape, spos.shape)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        clip, vis_idx = ctx.saved_tensors
+        B, T, H, W, pt, ps, n_vis, E, Tp, Lp = ctx.geom
+        dy = dy.contiguous()
+        dyb = cast_bf16(dy)
+        dw = db = dt = ds = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.zeros((E, 3 * pt * ps * ps), device=dy.device, dtype=F32)
+            L.check(_run("gemm_wgrad", 2.0 * dy.shape[0] * E * dw.shape[1], lambda: L.load().vmae_tubelet_embed_wgrad(
+                _p(clip), _p(vis_idx), _p(dyb), _p(dw), B, T, H, W, pt, ps, n_vis, E, _stream())), "vmae_tubelet_embed_wgrad")
+            _count()
+            dw = dw.reshape(ctx.shapes[0])
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = colsum(dyb)
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            dt = torch.zeros((Tp, E), device=dy.device, dtype=F32)
+            ds = torch.zeros((Lp, E), device=dy.device, dtype=F32)
+            L.check(L.load().vmae_pos_rows_bwd(_p(dy), _p(vis_idx), _p(dt), _p(ds), B, Tp, n_vis, E, _stream()), "vmae_pos_rows_bwd")
+            _count()
+            dt, ds = dt.reshape(ctx.shapes[1]), ds.reshape(ctx.shapes[2])
+        return None, None, dw, db, dt, ds, None, None
+
+
+def tubelet_embed_supported(ps, E):
+    return ps == 16 and E % 128 == 0 and 128 <= E <= 384
+
+
 class DecoderInputFn(torch.autograd.Function):
     """x_dec = visible ? z + (tpos + spos) : mask_token  (mae_vit_adapter.py:97-107). z bf16 rows; fp32 out [B,Tp*L,D]."""
 
@@ -1013,6 +1134,43 @@ class AdaptiveAvgPoolFn(torch.autograd.Function):
         L.check(L.load().vmae_adaptive_avgpool_bwd(_p(dout.float().contiguous()), _p(dx), N, H, W, Cc, s, _stream()), "vmae_adaptive_avgpool_bwd")
         _count()
         return dx, None
+
+
+class MeanPoolNoiseFn(torch.autograd.Function):
+    """z[b] = mean over tokens of x[b] (+ sigma * eps in the same kernel): bf16 [B, n, D] -> fp32 [B, D]. Gradient: dz / n broadcast."""
+
+    @staticmethod
+    def forward(ctx, x, sigma, seed, offset, eps_out):
+        _need_cuda(x)
+        B, n, D = x.shape
+        xb = cast_bf16(x)
+        out = torch.empty((B, D), device=x.device, dtype=F32)
+        if eps_out is not None:
+            assert eps_out.dtype == F32 and eps_out.is_contiguous() and eps_out.numel() == B * D and eps_out.is_cuda
+        L.check(L.load().vmae_meanpool_noise(_p(xb), _p(out), _p(eps_out), B, n, D, float(max(sigma, 0.0)), int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset),
+                                             _stream()), "vmae_meanpool_noise")
+        _count()
+        ctx.shape = (B, n, D)
+        ctx.in_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        B, n, D = ctx.shape
+        dx = torch.empty((B, n, D), device=dz.device, dtype=BF16)
+        L.check(L.load().vmae_se_scale(None, None, _p(dz.float().contiguous()), _p(dx), B, n, D, 1.0 / n, _stream()), "vmae_se_scale")
+        _count()
+        return (cast_f32(dx) if ctx.in_dtype == F32 else dx), None, None, None, None
+
+
+def meanpool_with_feature_noise(x, sigma=0.0, seed=None, eps_out=None):
+    if seed is None:
+        seed = torch.initial_seed()
+    off = 0
+    if sigma > 0:
+        off = _noise_offset[0]
+        _noise_offset[0] += (x.shape[0] * x.shape[2] + 3) // 4
+    return MeanPoolNoiseFn.apply(x, float(sigma), int(seed), off, eps_out)
 
 
 class SoftmaxCrossEntropyFn(torch.autograd.Function):

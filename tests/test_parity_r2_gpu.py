@@ -507,3 +507,209 @@ def test_nccl_bucketed_gradients_equal_single_rank_on_concatenated_batch(tmp_pat
     for k in ref:
         if float(ref[k].norm()) > 1e-6:
             assert float(got[k].norm()) == pytest.approx(float(ref[k].norm()), rel=2e-2), k
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# north_star bullet 4 / row a19: feature noise fused into the encoder-output epilogue; BASELINE config 4 (ViT-S finetune)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(10240, 384, 384), (300, 192, 384), (77, 104, 64)])
+def test_gemm_noise_epilogue_is_exact_given_the_drawn_normals(M, N, K):
+    """out = bf16(x W^T + b + sigma * eps) with eps returned by the kernel; and eps is the stream the stand-alone kernel draws for the
+    flattened [M, N] tensor under the same (seed, offset)."""
+    from ssl_vit_video_analytics_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) * 0.05
+    b = torch.randn(N, device=DEV, generator=g)
+    sigma, seed, off = 0.1, 4242, 17
+    eps = torch.empty(M, N, device=DEV)
+    y = ops.LinearNoiseFn.apply(x, w, b, sigma, seed, off, eps)
+    clean = ops.LinearFn.apply(x, w, b, 0)                                    # the same GEMM, bias epilogue, no noise (bf16)
+    ref32 = x.bfloat16().float() @ w.bfloat16().float().t() + b
+    want = (ref32 + sigma * eps).bfloat16()
+    # fp32 accumulation order differs from torch's matmul by ~1e-6 relative: allow one bf16 ulp on a handful of elements, none beyond
+    diff = (y.float() - want.float()).abs()
+    assert float(diff.max()) <= 2 ** -7 * float(want.float().abs().max())
+    assert float((diff > 0).float().mean()) < 0.02
+    assert float((y.float() - clean.float()).std()) == pytest.approx(sigma, rel=0.05)
+    ref_eps = torch.empty(M * N, device=DEV)
+    ops.GaussianNoiseFn.apply(torch.zeros(M * N, device=DEV), 1.0, seed, off, ref_eps)
+    assert torch.equal(eps.flatten(), ref_eps)                                # the stand-alone kernel's stream, bit for bit
+    # gradients are those of the Linear
+    xg = x.clone().requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    ops.LinearNoiseFn.apply(xg, wg, b, sigma, seed, off, None).float().sum().backward()
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ops.LinearFn.apply(xr, wr, b, 0).float().sum().backward()
+    assert torch.equal(xg.grad, xr.grad) and torch.allclose(wg.grad, wr.grad, rtol=1e-3, atol=1e-3 * float(wr.grad.abs().max()))
+
+
+def test_meanpool_with_feature_noise_kernel():
+    from ssl_vit_video_analytics_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(6)
+    x = torch.randn(5, 157, 384, device=DEV, generator=g).bfloat16().requires_grad_(True)
+    eps = torch.empty(5, 384, device=DEV)
+    z = ops.MeanPoolNoiseFn.apply(x, 0.2, 99, 3, eps)
+    ref = x.detach().float().mean(dim=1)
+    want = R.add_gaussian_noise(ref.double().cpu(), float(torch.tensor(0.2)), eps.double().cpu()).float()
+    assert torch.allclose(z.cpu(), want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ops.MeanPoolNoiseFn.apply(x, 0.0, 0, 0, None), ref, rtol=1e-5, atol=1e-6)
+    w = torch.randn(5, 384, device=DEV, generator=g)
+    (z * w).sum().backward()
+    assert float((x.grad.float() - (w / 157)[:, None, :].expand(5, 157, 384)).abs().max()) <= 1e-2 * float((w / 157).abs().max())
+
+
+def _classifier_case(cfg, B, num_classes, sigma):
+    from ssl_vit_video_analytics_b200.models import VideoMAEViTClassifier
+
+    torch.manual_seed(0)
+    model = VideoMAEViTClassifier(num_classes, cfg, noise_sigma=sigma)
+    sd = R.perturb_state_dict(model.state_dict(), seed=21)
+    model.load_state_dict(sd)
+    T, S = cfg["dataset"]["clip_len"], cfg["dataset"]["image_size"]
+    g = torch.Generator().manual_seed(8)
+    clip = torch.randn(B, 3, T, S, S, generator=g)
+    labels = torch.randint(0, num_classes, (B,), generator=g)
+    return model, sd, clip, labels
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_vit_s_finetune_classifier_with_fused_noise_vs_oracle(full):
+    """BASELINE config 4: ViT-S encoder on all tokens -> pooled embedding (+ sigma * eps in the pooling kernel) -> head -> fused CE.
+    full = the benchmark geometry (16x224x224, depth 12, 101 classes); otherwise a small geometry."""
+    from ssl_vit_video_analytics_b200.models.videomae_vit import DEFAULT_CONFIG
+
+    if full:
+        cfg, B, ncls = DEFAULT_CONFIG, 2, 101
+    else:
+        cfg = {"dataset": {"clip_len": 4, "image_size": 64}, "model": {"embed_dim": 384, "depth": 2, "num_heads": 6, "tubelet": [2, 16, 16],
+               "decoder_embed_dim": 384, "decoder_depth": 1, "decoder_num_heads": 6}}
+        B, ncls = 3, 11
+    sigma = 0.1
+    model, sd, clip, labels = _classifier_case(cfg, B, ncls, sigma)
+    model = model.to(DEV).train()
+    eps = torch.empty(B, 384, device=DEV)
+    model.noise_eps_out = eps
+    logits = model(clip.to(DEV))
+    loss = model.loss(logits, labels.to(DEV))
+    loss.backward()
+    m = cfg["model"]
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits_o, z_o = R.videomae_vit_classifier_forward(sdg, clip, m["depth"], m["num_heads"], tuple(m["tubelet"]), sigma, eps.cpu())
+    loss_o = F.cross_entropy(logits_o, labels)
+    loss_o.backward()
+    assert logits.shape == (B, ncls)
+    assert cosine(logits.float().cpu(), logits_o.detach()) >= COS_MIN
+    assert abs(float(loss) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o)) + 1e-3
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    ref = {k: v.grad for k, v in sdg.items() if v.grad is not None}
+    assert set(ours) == set(ref)
+    glob = cosine(torch.cat([ours[k].flatten() for k in ref]), torch.cat([ref[k].flatten() for k in ref]))
+    assert glob >= (0.995 if full else COS_MIN), glob
+    # MAE -> finetune hand-off: the encoder tensors of a VideoMAEViT state_dict load into .backbone
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+
+    mae = VideoMAEViT(cfg)
+    res = model.load_pretrained_mae(mae.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(model.backbone.blocks[0].attn.qkv.weight.cpu(), mae.blocks[0].attn.qkv.weight)
+
+
+def test_videomae_vit_encoder_output_noise_epilogue():
+    """VideoMAEViT with privacy.feature_noise_sigma > 0: enc_to_dec draws the noise in its GEMM epilogue; pred equals the oracle's pred
+    when the oracle adds sigma * eps (the returned normals) to its enc_to_dec output."""
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+    from ssl_vit_video_analytics_b200.models import VideoMAEViT
+
+    cfg = {"dataset": {"clip_len": 4, "image_size": 64}, "model": {"embed_dim": 384, "depth": 2, "num_heads": 6, "tubelet": [2, 16, 16],
+           "decoder_embed_dim": 384, "decoder_depth": 1, "decoder_num_heads": 6, "decoder_dropout": 0.0},
+           "ssl": {"mask_ratio": 0.75, "norm_pix_loss": True}, "privacy": {"feature_noise_sigma": 0.2}}
+    torch.manual_seed(0)
+    model = VideoMAEViT(cfg)
+    sd = R.perturb_state_dict(model.state_dict(), seed=4)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    clip = torch.randn(2, 3, 4, 64, 64, generator=g)
+    torch.manual_seed(3)
+    mask = get_tube_mask(2, 2, 16, 0.75)
+    model = model.to(DEV).train()
+    eps = torch.empty(2 * 2 * 4, 384, device=DEV)
+    model.noise_eps_out = eps
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = model(clip.to(DEV), mask.to(DEV))
+    # oracle: bias of enc_to_dec shifted per row is not expressible, so add the noise by hooking F.linear's output through a per-call patch
+    m = cfg["model"]
+    calls = {"n": 0}
+    orig = R.F.linear
+
+    def patched(x, w, b=None):
+        y = orig(x, w, b)
+        if w is sd["enc_to_dec.weight"]:
+            calls["n"] += 1
+            y = y + 0.2 * eps.cpu().view(y.shape)
+        return y
+
+    R.F.linear = patched
+    try:
+        pred_o = R.videomae_vit_forward(sd, clip, mask, m["depth"], m["num_heads"], m["decoder_depth"], m["decoder_num_heads"], (2, 16, 16))
+    finally:
+        R.F.linear = orig
+    assert calls["n"] == 1
+    assert cosine(pred.float().cpu(), pred_o) >= COS_MIN
+    model.feature_noise_sigma = 0.0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        pred0 = model(clip.to(DEV), mask.to(DEV))
+    assert cosine(pred0.float().cpu(), pred_o) < cosine(pred.float().cpu(), pred_o)      # the noise really went through the decoder
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# north_star bullet 1 / NS-2: tubelet Conv3d of the visible tubes as ONE implicit-GEMM kernel (TMA 5-D boxes, bias + pos epilogue)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,S,pt,ratio", [(2, 4, 64, 2, 0.75), (3, 16, 224, 2, 0.9), (1, 2, 32, 1, 0.5), (5, 8, 112, 2, 0.0)])
+def test_tubelet_embed_implicit_gemm_fwd_and_grads(B, T, S, pt, ratio):
+    from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
+
+    E, ps = 384, 16
+    Tp, Lp = T // pt, (S // ps) ** 2
+    g = torch.Generator().manual_seed(13)
+    clip = torch.randn(B, 3, T, S, S, generator=g)
+    w = torch.randn(E, 3, pt, ps, ps, generator=g) * 0.03
+    bias = torch.randn(E, generator=g) * 0.1
+    tpos = torch.randn(1, Tp, 1, E, generator=g) * 0.02
+    spos = torch.randn(1, 1, Lp, E, generator=g) * 0.02
+    torch.manual_seed(14)
+    mask = get_tube_mask(B, Tp, Lp, ratio)
+    vis = visible_indices(mask)
+    n_vis = vis.shape[1]
+    rows = B * Tp * n_vis
+    # fp32 reference on the bf16-rounded operands (what the tensor cores see): Conv3d -> + pos -> gather (oracle composition)
+    tok = F.conv3d(clip.bfloat16().float(), w.bfloat16().float(), bias, stride=(pt, ps, ps)).flatten(3).permute(0, 2, 3, 1) + (tpos + spos)
+    idx = vis.long()[:, None, :, None].expand(B, Tp, n_vis, E)
+    ref = torch.gather(tok, 2, idx).reshape(rows, E)
+    dev_args = [t.to(DEV).requires_grad_(t.is_floating_point() and i > 1) for i, t in enumerate((clip, vis, w, bias, tpos, spos))]
+    out = ops.TubeletEmbedFn.apply(*dev_args, pt, ps)
+    assert out.shape == (rows, E) and out.dtype == torch.float32
+    assert float((out.cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-4
+    # same arithmetic as the two-kernel form (gather kernel + GEMM with fp32 residual rows)
+    patches, pos_rows = ops.TubeletGatherFn.apply(dev_args[0], dev_args[1], dev_args[4], dev_args[5], pt, ps)
+    two = ops.LinearResidualF32Fn.apply(patches, dev_args[2], dev_args[3], pos_rows)
+    assert float((out - two).abs().max()) <= 1e-4 * float(two.abs().max()) + 1e-5
+    # gradients: weight (implicit-GEMM wgrad re-gathering the boxes), bias, both positional tables
+    dy = torch.randn(rows, E, generator=g)
+    out.backward(dy.to(DEV))
+    patches_ref = R.patchify(clip, pt, ps)                                              # [B, Tp*Lp, pt*ps*ps*3] in (dt, py, px, c) order
+    pr = patches_ref.reshape(B, Tp, Lp, pt, ps, ps, 3).permute(0, 1, 2, 6, 3, 4, 5).reshape(B, Tp, Lp, -1)   # -> (c, dt, py, px) = Conv3d weight order
+    a = torch.gather(pr, 2, vis.long()[:, None, :, None].expand(B, Tp, n_vis, pr.shape[-1])).reshape(rows, -1)
+    dyb = dy.bfloat16().float()
+    dw_ref = (dyb.t() @ a.bfloat16().float()).reshape(w.shape)
+    gw = dev_args[2].grad.cpu()
+    assert float((gw - dw_ref).abs().max()) <= 3e-3 * float(dw_ref.abs().max()) + 1e-4, float((gw - dw_ref).abs().max())
+    assert torch.allclose(dev_args[3].grad.cpu(), dyb.sum(0), rtol=1e-3, atol=1e-3 * float(dyb.sum(0).abs().max()))
+    dt_ref = dy.reshape(B, Tp, n_vis, E).sum(dim=(0, 2)).reshape(tpos.shape)
+    assert torch.allclose(dev_args[4].grad.cpu(), dt_ref, rtol=1e-4, atol=1e-4 * float(dt_ref.abs().max()))
+    ds_ref = torch.zeros(Lp, E).index_add_(0, vis.long()[:, None, :].expand(B, Tp, n_vis).reshape(-1), dy)
+    assert torch.allclose(dev_args[5].grad.cpu().reshape(Lp, E), ds_ref, rtol=1e-4, atol=1e-4 * float(ds_ref.abs().max()) + 1e-6)
