@@ -181,6 +181,67 @@ def time_cpu_reference_model_a(steps, warmup, threads):
     return 2 * steps / dt, dt / steps * 1e3
 
 
+def time_model_a(dev, steps, warmup, peaks):
+    """Secondary line: the DROP-IN model (reference TinyVideoMAE on the TinyViT-21M encoder, the path with a live reference) at the
+    reference's own configs/ssl_mae.yaml shapes (B=40, T=16, 112x112, patch 8, mask 0.9), perturbed init,
+    forward + fused loss + backward + FusedAdamW on our kernels, eager launches. 740.3 GFLOP per clip and step."""
+    from ssl_vit_video_analytics_b200 import ops
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask
+    from ssl_vit_video_analytics_b200.models import TinyVideoMAE, tiny_vit_21m_variant
+    from ssl_vit_video_analytics_b200.optim import FusedAdamW
+    from ssl_vit_video_analytics_b200.parallel import GradientBucketer
+    from ssl_vit_video_analytics_b200.train_ssl_mae import mae_step_loss
+
+    B = 40
+    tcfg = {"dataset": {"clip_len": 16, "image_size": 112},
+            "model": {"decoder_embed_dim": 384, "decoder_depth": 4, "decoder_num_heads": 6, "decoder_dropout": 0.0}}
+    torch.manual_seed(0)
+    model = TinyVideoMAE(tiny_vit_21m_variant(img_size=112, use_checkpoint=False, drop_path_rate=0.0), tcfg)
+    gen = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(".bn.weight"):
+                p.copy_(torch.rand(p.shape, generator=gen) + 0.5)
+            elif name.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.02)
+    model = model.to(dev).train()
+    ddp = GradientBucketer(model, bucket_mb=32.0, exclude=("encoder.stages.3.",), broadcast=False)
+    ddp.world = 1
+    opt = FusedAdamW([p for n, p in model.named_parameters() if not n.startswith("encoder.stages.3.")], lr=5e-4, weight_decay=0.05)
+    g = torch.Generator().manual_seed(0)
+    clip = torch.randn(B, 3, 16, 112, 112, generator=g).to(dev)
+    torch.manual_seed(42)
+    mask = get_tube_mask(B, 16, 196, 0.9).to(dev)
+
+    def step():
+        ddp.zero_grad()
+        loss = mae_step_loss(model, clip, mask, True)[0]
+        loss.backward()
+        ddp.finish_gradient_sync()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    val = B / (ms / 1e3)
+    out = {"metric": "tinyvideomae_pretrain_clips_per_sec", "value": val, "unit": UNIT, "ms_per_step": ms, "steps": steps, "per_gpu_batch": B,
+           "workload": "drop-in TinyVideoMAE (TinyViT-21M encoder), 16x112x112, patch 8, mask 0.9 (configs/ssl_mae.yaml), use_checkpoint=False, drop-path/dropout 0, perturbed init, eager launches",
+           "step_gflop_per_clip": 740.3, "frac_of_tensor_roofline": (B * 740.3 / 1e3) / (ms / 1e3) / peaks["bf16_tflops_sustained"],
+           "final_loss": float(loss.detach()), "gpu_launches_per_step": (ops.launch_count() - n0) / steps}
+    del model, ddp, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def time_gpu_eager(cfg, batch, steps, warmup, dev):
     """BASELINE.md §3 row "GPU-eager-ref": the SAME model-B step written in plain PyTorch (the oracle restatement: nn.functional
     conv3d / linear / layer_norm / scaled_dot_product_attention / gelu, i.e. cuDNN + cuBLAS + flash-SDPA), bf16 autocast, same batch,
@@ -556,9 +617,12 @@ def run_ours(args, cfg):
                   "note": "same loop fed with pinned uint8 frames [B,T,H,W,3]; ToTensor + Normalize + channel order on the GPU (vmae_frames_to_clip)"}
 
     # ---- roofline leg: the same step with CUDA events around every launch of ours (separate region: events perturb)
+    # Every profiled step is queued behind a ~30 ms spin kernel: the host needs ~12 ms to enqueue the ~400 eager launches of a
+    # step, so without the head start the GPU catches up with the host and the event pairs also measure the host's launch gaps.
     ddp.defer_comm = False
     ops.profile_start()
     for _ in range(2):
+        torch.cuda._sleep(int(30e-3 * 1.9e9))
         eager_step(clip_d)
     prof = ops.profile_stop()
     for v in prof.values():
@@ -620,6 +684,12 @@ def run_ours(args, cfg):
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if world == 1 and not args.no_model_a and args.workload == "vit_s":
+        try:
+            torch.cuda.empty_cache()
+            line["model_a"] = time_model_a(dev, 5, 3, peaks)
+        except Exception as ex:
+            line["model_a"] = {"value": None, "unit": UNIT, "workload": f"failed: {ex!r}"}
     if world == 1 and not args.no_gpu_eager and args.workload == "vit_s":
         try:
             torch.cuda.empty_cache()
@@ -767,6 +837,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model-a", action="store_true", help="skip the secondary line of the drop-in TinyVideoMAE (configs/ssl_mae.yaml shapes)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the plain-PyTorch (cuBLAS/cuDNN/SDPA) comparator leg")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused = optim.FusedAdamW (default); torch = torch.optim.AdamW(fused=True), for A/B runs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],

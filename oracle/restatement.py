@@ -288,7 +288,7 @@ def videomae_vit_forward(sd: SD, clip: Tensor, mask: Tensor, depth: int, heads: 
     x = F.layer_norm(x, (E,), sd["norm.weight"], sd["norm.bias"], 1e-5)
     z = F.linear(x, sd["enc_to_dec.weight"], sd["enc_to_dec.bias"]).view(B, Tp, n_vis, -1)
     D = z.shape[-1]
-    full = torch.zeros(B, Tp, Lp, D, dtype=z.dtype)
+    full = torch.zeros(B, Tp, Lp, D, dtype=z.dtype, device=z.device)
     full = full.scatter(2, idx[:, None, :, None].expand(B, Tp, n_vis, D), z)
     full = full + (sd["temporal_pos_embed"] + sd["spatial_pos_embed"])
     m = mask.unsqueeze(-1).type_as(full)

@@ -62,7 +62,7 @@ __device__ __forceinline__ void convert_rows(uint32_t staging, uint32_t tile, in
 __global__ void __launch_bounds__(te::THREADS, 1)
 tubelet_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_clip, const __grid_constant__ CUtensorMap map_w, const int* __restrict__ vis_idx,
                          const float* __restrict__ bias, const float* __restrict__ tpos, const float* __restrict__ spos, float* __restrict__ out,
-                         const te::Geom g) {
+                         const te::Geom g, const int rows_per_cta) {
   using namespace te;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,7 +77,10 @@ tubelet_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_clip, const __g
   const uint32_t acc_full = bar + 64, tmem_ptr_addr = bar + 72;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
+  // A CTA owns rows_per_cta <= 128 tubelet rows (the UMMA tile is always 128 rows; the unused rows cost tensor time only, and this
+  // kernel is bound by the TMA gather: ~90 cycles per 256-byte box). The host sizes rows_per_cta so that ONE wave covers all SMs.
+  const int m0 = blockIdx.x * rows_per_cta;
+  const int m_end = min(m0 + rows_per_cta, g.rows);
   const int nkb = g.K / BK;
   const int n1 = g.E < 256 ? g.E : 256, n2 = g.E - n1;
 
@@ -103,12 +106,11 @@ tubelet_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_clip, const __g
     // ---- producer: weight tile by one elected lane, gather boxes by all lanes (rows lane, lane+32, lane+64, lane+96)
     int cb[4], ct[4], cy[4], cx[4];
     bool ok[4];
-    int valid = g.rows - m0;
-    valid = valid > BM ? BM : valid;
+    const int valid = m_end - m0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int m = m0 + lane + 32 * r;
-      ok[r] = m < g.rows;
+      ok[r] = m < m_end;
       int b = 0, tp = 0, l = 0;
       if (ok[r]) row_coords(g, vis_idx, m, b, tp, l);
       cb[r] = b; ct[r] = tp * g.pt; cy[r] = (l / g.wp) * PS; cx[r] = (l % g.wp) * PS;
@@ -168,7 +170,7 @@ tubelet_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_clip, const __g
     tc_fence_after();
     const int quad = warp & 3, half = cw >> 2;
     const int m = m0 + quad * 32 + lane;
-    const bool live = m < g.rows;
+    const bool live = m < m_end;
     int b = 0, tp = 0, l = 0;
     if (live) row_coords(g, vis_idx, m, b, tp, l);
     const int ncol = g.E / 2;
@@ -407,8 +409,11 @@ extern "C" int vmae_tubelet_embed_fwd(const float* clip, const int* vis_idx, con
     VMAE_CUDA(cudaFuncSetAttribute(tubelet_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, te::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = (g.rows + te::BM - 1) / te::BM;
-  tubelet_embed_fwd_kernel<<<grid, te::THREADS, te::SMEM_BYTES, (cudaStream_t)stream>>>(m_clip, m_w, vis_idx, bias, temporal_pos, spatial_pos, out, g);
+  int rpc = (g.rows + num_sms() - 1) / num_sms();   // one wave: every SM gathers an equal share of the rows
+  rpc = (rpc + 7) / 8 * 8;
+  if (rpc > te::BM) rpc = te::BM;
+  const int grid = (g.rows + rpc - 1) / rpc;
+  tubelet_embed_fwd_kernel<<<grid, te::THREADS, te::SMEM_BYTES, (cudaStream_t)stream>>>(m_clip, m_w, vis_idx, bias, temporal_pos, spatial_pos, out, g, rpc);
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
 }
@@ -437,7 +442,7 @@ extern "C" int vmae_tubelet_embed_wgrad(const float* clip, const int* vis_idx, c
   }
   const int total_steps = (g.rows + tw::BR - 1) / tw::BR;
   const int tiles = (E / tw::BN_OUT) * (g.K / tw::BKC);
-  int splits = (num_sms() + tiles - 1) / tiles;                 // about one CTA per SM
+  int splits = num_sms() / tiles;                               // one wave: at most one CTA per SM
   if (splits > total_steps) splits = total_steps;
   if (splits < 1) splits = 1;
   const int per = (total_steps + splits - 1) / splits;
