@@ -20,6 +20,7 @@
 // epilogue reads (fp32 residual, bf16 pre-activation for gelu') arrive the same way: a TMA load of the next chunk's box
 // is in flight while the current chunk is processed. The threads therefore issue no global loads/stores at all; all
 // global traffic is full-line bulk copies and edge tiles are clipped by the TMA unit.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "philox.cuh"
@@ -30,8 +31,14 @@ namespace vmae {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;
+constexpr int GEMM_EPI_WARPS = 8;   // default: two epilogue warps per TMEM lane quadrant
+// EW = 12 (three per quadrant, 64 columns each of a 192-wide tile) is instantiated for the epilogues with an input stream or real
+// arithmetic. Measured at M = 100352 (us, 8 -> 12 warps): gelu' multiply (dgrad of fc2) 161 -> 156, 131 -> 117 (N = 1152), 52 -> 45 (N = 384):
+// used by default; fp32 residual 72 -> 68 (K = 384) but 135 -> 149 (K = 1536: the larger staging leaves 3 instead of 4 operand stages):
+// not used; GELU with the saved gelu' 177 -> 184: no gain, because that kernel is not epilogue-bound but HBM-WRITE-bound — it writes
+// 616 MB (activation + gelu'), and a write-only stream on this part tops out at 3.9 TB/s (tools/bw_probe.py: memset 3.9, copy 6.5,
+// read-only 5.9 TB/s), i.e. 158 us.
+constexpr int gemm_threads(int ew) { return (2 + ew) * 32; }
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 enum : int {
@@ -45,7 +52,7 @@ enum : int {
                        //            keyed on (seed, offset + flattened element index / 4): the stream of the stand-alone kernel)
 };
 
-template <int EPI>
+template <int EPI, int EW = GEMM_EPI_WARPS>
 struct EpiTraits {
   static constexpr bool OUT_F32 = (EPI == EPI_F32 || EPI == EPI_F32_RESID || EPI == EPI_F32_ACCUM);
   static constexpr bool HAS_IN = (EPI == EPI_BF16_DGELU || EPI == EPI_F32_RESID);
@@ -53,7 +60,7 @@ struct EpiTraits {
   static constexpr int BOX_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);     // one 32x32 staging box
   static constexpr int BUF_BYTES = BOX_BYTES * (DUAL ? 2 : 1);     // per buffer (dual: activation + pre-activation)
   static constexpr int WARP_BYTES = 2 * BUF_BYTES;                  // double buffered
-  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * WARP_BYTES;
+  static constexpr int STAGING_BYTES = EW * WARP_BYTES;
 };
 
 struct GemmParams {
@@ -67,12 +74,12 @@ struct GemmParams {
   float* eps_out;     // optional fp32 [M, N] (dense): the unit normals that were drawn (exact-parity tests)
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int EW = GEMM_EPI_WARPS>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = EpiTraits<EPI>::STAGING_BYTES;
+  static constexpr int STAGING_BYTES = EpiTraits<EPI, EW>::STAGING_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int ONES_BYTES = (EPI == EPI_F32_ACCUM) ? 2048 : 0;   // 16 x 64 bf16 tile of 1.0 (row-sum UMMA operand)
   static constexpr int AVAIL = GEMM_SMEM_LIMIT - STAGING_BYTES - ONES_BYTES - BAR_BYTES - 1024;
@@ -138,12 +145,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float
 __device__ __forceinline__ uint32_t box_f32_slot(uint32_t box, int r, int j) { return box + r * 128 + ((j ^ (r & 7)) << 4); }
 __device__ __forceinline__ uint32_t box_bf16_slot(uint32_t box, int r, int j) { return box + r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
-template <int BLOCK_N, int A_MN, int B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BLOCK_N, int A_MN, int B_MN, int EPI, int EW = GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, EPI>;
-  using ET = EpiTraits<EPI>;
+  using Cfg = GemmCfg<BLOCK_N, EPI, EW>;
+  using ET = EpiTraits<EPI, EW>;
+  static_assert(EW % 4 == 0 && BLOCK_N % (EW / 4 * 32) == 0, "every TMEM lane quadrant gets EW/4 warps with whole 32-column chunks");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -154,8 +162,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (18 + a); };
-  auto in_bar = [&](int w, int b) { return bar_base + 8u * (20 + 2 * w + b); };  // 16 barriers: epilogue-input boxes
-  const uint32_t tmem_ptr_addr = bar_base + 8u * 40;
+  auto in_bar = [&](int w, int b) { return bar_base + 8u * (20 + 2 * w + b); };  // 2 * EW barriers: epilogue-input boxes
+  static_assert(20 + 2 * EW <= 60, "barrier slots");
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 60;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -178,9 +187,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
+      mbar_init(tempty_bar(a), EW);
     }
-    for (int w = 0; w < GEMM_EPI_WARPS; ++w) {
+    for (int w = 0; w < EW; ++w) {
       mbar_init(in_bar(w, 0), 1);
       mbar_init(in_bar(w, 1), 1);
     }
@@ -303,8 +312,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
-    const int half = ew >> 2;               // which half of the tile's columns
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const int half = ew >> 2;               // which slice of the tile's columns (EW / 4 slices)
+    constexpr int COLS_PER_WARP = BLOCK_N / (EW / 4);
     constexpr int CHUNKS = COLS_PER_WARP / 32;
     const uint32_t my_staging = staging_base + ew * ET::WARP_BYTES;
     const int r = lane;                     // row inside the 32-row box
@@ -480,16 +489,16 @@ struct GemmMaps {
   CUtensorMap a, b, out, aux;
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, int EPI>
+template <int BLOCK_N, int A_MN, int B_MN, int EPI, int EW = GEMM_EPI_WARPS>
 static int launch_gemm(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, EPI>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, EPI, EW>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, EW>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  VMAE_CUDA(launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, m.a, m.b, m.out, m.aux, p));
+  VMAE_CUDA(launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(gemm_threads(EW)), Cfg::SMEM_BYTES, stream, m.a, m.b, m.out, m.aux, p));
   return VMAE_OK;
 }
 
@@ -500,8 +509,23 @@ static int dispatch_major(int a_major, int b_major, const GemmMaps& m, const Gem
   return launch_gemm<BLOCK_N, 1, 1, EPI>(m, p, grid, stream);
 }
 
+// Epilogues that run with 12 epilogue warps on 192-wide tiles (bit mask over EPI ids; VMAE_GEMM_EW12 overrides for A/B runs)
+static int ew12_mask() {
+  static const int mask = [] { const char* e = getenv("VMAE_GEMM_EW12"); return e ? atoi(e) : (1 << EPI_BF16_DGELU); }();
+  return mask;
+}
+static bool use_ew12(int epi, int a_major) { return a_major == VMAE_MAJOR_K && ((ew12_mask() >> epi) & 1); }
+
 template <int BLOCK_N>
 static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  if constexpr (BLOCK_N == 192) {
+    if (use_ew12(epi, a_major)) {
+      const bool bmn = b_major == VMAE_MAJOR_MN;
+      if (epi == EPI_BF16_GELU && !bmn) return launch_gemm<192, 0, 0, EPI_BF16_GELU, 12>(m, p, grid, stream);
+      if (epi == EPI_BF16_DGELU) return bmn ? launch_gemm<192, 0, 1, EPI_BF16_DGELU, 12>(m, p, grid, stream) : launch_gemm<192, 0, 0, EPI_BF16_DGELU, 12>(m, p, grid, stream);
+      if (epi == EPI_F32_RESID && !bmn) return launch_gemm<192, 0, 0, EPI_F32_RESID, 12>(m, p, grid, stream);
+    }
+  }
   switch (epi) {
     case EPI_BF16: return dispatch_major<BLOCK_N, EPI_BF16>(a_major, b_major, m, p, grid, stream);
     case EPI_BF16_GELU: return dispatch_major<BLOCK_N, EPI_BF16_GELU>(a_major, b_major, m, p, grid, stream);
@@ -517,7 +541,8 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
 
 // Tile width: minimise (rounds over the SMs) x (time of one tile). A tile's time is ~ BLOCK_N plus a fixed part
 // (pipeline fill, epilogue tail); wide tiles re-read A less, narrow tiles quantise better when M is small.
-static int pick_block_n(int M, int N, int k_splits, bool accumulate) {
+static int pick_block_n(int M, int N, int k_splits, bool accumulate, bool ew12) {
+  if (ew12 && N >= 192) return 192;   // the 12-warp epilogue exists for 192-wide tiles
   const int cands[3] = {256, 192, 128};
   const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int sms = num_sms();
@@ -598,7 +623,8 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
     k_splits = (num_kb + per - 1) / per;
   }
 
-  const int block_n = pick_block_n(M, N, k_splits, accumulate != 0);
+  const bool ew12 = use_ew12(epi, a_major) && !(epi == EPI_BF16_GELU && b_major == VMAE_MAJOR_MN) && !(epi == EPI_F32_RESID && b_major == VMAE_MAJOR_MN);
+  const int block_n = pick_block_n(M, N, k_splits, accumulate != 0, ew12);
   GemmMaps maps;
   int rc;
   if (a_major == VMAE_MAJOR_K) {
