@@ -28,12 +28,19 @@ extern "C" {
 
 #define VMAE_DTYPE_BF16 0
 #define VMAE_DTYPE_F32 1
+#define VMAE_DTYPE_U8 2 /* only as the 8-bit gelu' side tensor of the GEMM (VMAE_ACT_GELU_Q8 / VMAE_ACT_AUX_Q8) */
 
 #define VMAE_MAJOR_K 0  /* contraction dimension contiguous: A is [M,K], B is [N,K] row-major */
 #define VMAE_MAJOR_MN 1 /* M/N dimension contiguous:        A is [K,M], B is [K,N] row-major */
 
 #define VMAE_ACT_NONE 0
 #define VMAE_ACT_GELU 1 /* exact erf GELU, as nn.GELU() / activation="gelu" in the reference */
+/* The saved gelu'(pre-activation) as ONE BYTE per element: q = round((g + 0.13) * 255 / 1.26), g in [-0.129, 1.129]; step 0.0049, i.e.
+ * |error| <= 0.0025 — the size of bf16 rounding for the typical g ~ 0.5..1. The dual-output GELU GEMM is bound by HBM WRITE bandwidth
+ * (3.9 TB/s write-only on this part): 462 MB instead of 616 MB per fc1 launch at batch 64.
+ *   forward: act = VMAE_ACT_GELU_Q8, aux_out = uint8 [M, ld_aux_out];   dgrad: act = VMAE_ACT_AUX_Q8, aux_in = that uint8 tensor. */
+#define VMAE_ACT_GELU_Q8 2
+#define VMAE_ACT_AUX_Q8 3
 
 /* ---- library ------------------------------------------------------------------------------------------------- */
 const char* vmae_last_error(void);

@@ -13,7 +13,8 @@ LIB_PATH = Path(os.environ.get("VMAE_LIB_OVERRIDE") or (_PKG / "lib" / "libvmae_
 
 DTYPE_BF16, DTYPE_F32 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_GELU_Q8, ACT_AUX_Q8 = 0, 1, 2, 3
+DTYPE_U8 = 2
 
 _p, _ll, _i, _f, _ull = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_ulonglong
 

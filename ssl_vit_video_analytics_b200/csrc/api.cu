@@ -63,7 +63,7 @@ int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uin
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return fail(VMAE_ERR_BAD_ARG, "TMA base pointer %p not 16-byte aligned", base);
   for (int i = 0; i + 1 < rank; ++i)
     if (gstr[i] % 16 != 0) return fail(VMAE_ERR_BAD_ARG, "TMA stride %llu (dim %d) not a multiple of 16 bytes", (unsigned long long)gstr[i], i + 1);
-  CUresult r = fn(out, dtype == VMAE_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+  CUresult r = fn(out, dtype == VMAE_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == VMAE_DTYPE_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

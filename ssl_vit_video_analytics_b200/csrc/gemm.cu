@@ -48,6 +48,8 @@ enum : int {
   EPI_F32 = 3,         // out f32  = acc (+bias)
   EPI_F32_RESID = 4,   // out f32  = acc (+bias) + residual
   EPI_F32_ACCUM = 5,   // out f32 += acc            (TMA reduce-add; split-K)
+  EPI_BF16_GELU_Q8 = 7,   // EPI_BF16_GELU with gelu' stored as uint8 (see VMAE_ACT_GELU_Q8 in vmae.h)
+  EPI_BF16_DGELU_Q8 = 8,  // EPI_BF16_DGELU reading that uint8 tensor
   EPI_BF16_NOISE = 6,  // out bf16 = acc (+bias) + sigma * N(0,1)  (privacy/feature_noise.py:4-7 fused into the producing GEMM; Philox
                        //            keyed on (seed, offset + flattened element index / 4): the stream of the stand-alone kernel)
 };
@@ -55,8 +57,10 @@ enum : int {
 template <int EPI, int EW = GEMM_EPI_WARPS>
 struct EpiTraits {
   static constexpr bool OUT_F32 = (EPI == EPI_F32 || EPI == EPI_F32_RESID || EPI == EPI_F32_ACCUM);
-  static constexpr bool HAS_IN = (EPI == EPI_BF16_DGELU || EPI == EPI_F32_RESID);
-  static constexpr bool DUAL = (EPI == EPI_BF16_GELU);
+  static constexpr bool HAS_IN = (EPI == EPI_BF16_DGELU || EPI == EPI_F32_RESID || EPI == EPI_BF16_DGELU_Q8);
+  static constexpr bool DUAL = (EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_Q8);
+  static constexpr bool Q8 = (EPI == EPI_BF16_GELU_Q8 || EPI == EPI_BF16_DGELU_Q8);
+  static constexpr int IN_BYTES = (EPI == EPI_BF16_DGELU_Q8) ? 32 * 32 : 32 * 32 * (OUT_F32 ? 4 : 2);   // bytes of the epilogue-input box
   static constexpr int BOX_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);     // one 32x32 staging box
   static constexpr int BUF_BYTES = BOX_BYTES * (DUAL ? 2 : 1);     // per buffer (dual: activation + pre-activation)
   static constexpr int WARP_BYTES = 2 * BUF_BYTES;                  // double buffered
@@ -83,7 +87,10 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 512;
   static constexpr int ONES_BYTES = (EPI == EPI_F32_ACCUM) ? 2048 : 0;   // 16 x 64 bf16 tile of 1.0 (row-sum UMMA operand)
   static constexpr int AVAIL = GEMM_SMEM_LIMIT - STAGING_BYTES - ONES_BYTES - BAR_BYTES - 1024;
-  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
+#ifndef VMAE_GEMM_MAX_STAGES
+#define VMAE_GEMM_MAX_STAGES 8
+#endif
+  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > VMAE_GEMM_MAX_STAGES ? VMAE_GEMM_MAX_STAGES : (AVAIL / STAGE_BYTES);
   static constexpr int TMEM_NEED = 2 * BLOCK_N + ((EPI == EPI_F32_ACCUM) ? 32 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + ONES_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
@@ -331,7 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (ET::HAS_IN && lane == 0 && static_cast<int>(blockIdx.x) < total_units) {
       int gm, gn;
       chunk_coords(blockIdx.x, 0, gm, gn);
-      mbar_expect_tx(in_bar(ew, 0), ET::BOX_BYTES);
+      mbar_expect_tx(in_bar(ew, 0), ET::IN_BYTES);
       tma_load_2d(my_staging, &tma_aux, in_bar(ew, 0), gn, gm);
     }
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -366,7 +373,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        if (EPI != EPI_F32_ACCUM && EPI != EPI_BF16_DGELU && p.bias != nullptr) {
+        if (EPI != EPI_F32_ACCUM && EPI != EPI_BF16_DGELU && EPI != EPI_BF16_DGELU_Q8 && p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (gn + j < p.N) {  // N % 8 == 0: a float4 is either fully inside or fully outside
@@ -391,8 +398,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         if (ET::HAS_IN) mbar_wait(in_bar(ew, b), (item >> 1) & 1u);
-        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_NOISE) {
-          if (EPI == EPI_BF16_GELU) {
+        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_NOISE || EPI == EPI_BF16_GELU_Q8) {
+          if (EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_Q8) {
             // one evaluation of Phi(x) serves both gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x); the derivative is
             // what backward needs, so it is stored instead of the pre-activation (same bytes, and the dgrad epilogue
             // becomes a plain multiply)
@@ -420,15 +427,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               up2(fma2(xc2, pdf2, cdf2), d[j], d[j + 1]);
               up2(mul2(x2, cdf2), v[j], v[j + 1]);
             }
+            if (EPI == EPI_BF16_GELU_Q8) {
+              // gelu' in [-0.129, 1.129] -> one byte: q = rn((g + 0.13) * 255 / 1.26); the box is 32 rows x 32 bytes, unswizzled
+              uint32_t q[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts_u4(box_bf16_slot(buf + ET::BOX_BYTES, r, j), pack2(d[8 * j], d[8 * j + 1]), pack2(d[8 * j + 2], d[8 * j + 3]),
-                     pack2(d[8 * j + 4], d[8 * j + 5]), pack2(d[8 * j + 6], d[8 * j + 7]));
+              for (int j = 0; j < 8; ++j) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float t = fminf(fmaxf(fmaf(d[4 * j + k], 202.38095f, 26.309524f), 0.f), 255.f);
+                  w |= static_cast<uint32_t>(__float2int_rn(t)) << (8 * k);
+                }
+                q[j] = w;
+              }
+              sts_u4(buf + ET::BOX_BYTES + r * 32, q[0], q[1], q[2], q[3]);
+              sts_u4(buf + ET::BOX_BYTES + r * 32 + 16, q[4], q[5], q[6], q[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts_u4(box_bf16_slot(buf + ET::BOX_BYTES, r, j), pack2(d[8 * j], d[8 * j + 1]), pack2(d[8 * j + 2], d[8 * j + 3]),
+                       pack2(d[8 * j + 4], d[8 * j + 5]), pack2(d[8 * j + 6], d[8 * j + 7]));
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts_u4(box_bf16_slot(buf, r, j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
                    pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+        } else if (EPI == EPI_BF16_DGELU_Q8) {
+          // the input box holds 32 rows x 32 bytes of quantised gelu' (unswizzled); the bf16 result goes to the same buffer's
+          // 64-byte-row swizzled layout, which starts at the same address: read this row's 32 bytes first, then write
+          const uint4 qa = lds_u4(buf + r * 32), qb = lds_u4(buf + r * 32 + 16);
+          __syncwarp();   // every lane has read its bytes before any lane's (larger) output row overwrites the region
+          const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          float h[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[4 * j + k] = fmaf(static_cast<float>((qw[j] >> (8 * k)) & 0xffu), 0.0049411765f, -0.13f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts_u4(box_bf16_slot(buf, r, j), pack2(v[8 * j] * h[8 * j], v[8 * j + 1] * h[8 * j + 1]), pack2(v[8 * j + 2] * h[8 * j + 2], v[8 * j + 3] * h[8 * j + 3]),
+                   pack2(v[8 * j + 4] * h[8 * j + 4], v[8 * j + 5] * h[8 * j + 5]), pack2(v[8 * j + 6] * h[8 * j + 6], v[8 * j + 7] * h[8 * j + 7]));
         } else if (EPI == EPI_BF16_DGELU) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -454,7 +493,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
           if (EPI == EPI_F32_ACCUM) tma_reduce_add_2d(&tma_out, buf, gn, gm);
           else tma_store_2d(&tma_out, buf, gn, gm);
-          if (EPI == EPI_BF16_GELU) tma_store_2d(&tma_aux, buf + ET::BOX_BYTES, gn, gm);
+          if (EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_Q8) tma_store_2d(&tma_aux, buf + ET::BOX_BYTES, gn, gm);
           tma_store_commit();
           tma_store_wait_read<1>();  // the other buffer (previous item) has been read out -> free for reuse
           if (ET::HAS_IN) {
@@ -464,7 +503,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (nunit < total_units) {
               int ngm, ngn;
               chunk_coords(nunit, nc, ngm, ngn);
-              mbar_expect_tx(in_bar(ew, b ^ 1), ET::BOX_BYTES);
+              mbar_expect_tx(in_bar(ew, b ^ 1), ET::IN_BYTES);
               tma_load_2d(my_staging + (b ^ 1) * ET::BUF_BYTES, &tma_aux, in_bar(ew, b ^ 1), ngn, ngm);
             }
           }
@@ -511,7 +550,7 @@ static int dispatch_major(int a_major, int b_major, const GemmMaps& m, const Gem
 
 // Epilogues that run with 12 epilogue warps on 192-wide tiles (bit mask over EPI ids; VMAE_GEMM_EW12 overrides for A/B runs)
 static int ew12_mask() {
-  static const int mask = [] { const char* e = getenv("VMAE_GEMM_EW12"); return e ? atoi(e) : (1 << EPI_BF16_DGELU); }();
+  static const int mask = [] { const char* e = getenv("VMAE_GEMM_EW12"); return e ? atoi(e) : ((1 << EPI_BF16_DGELU) | (1 << EPI_BF16_DGELU_Q8)); }();
   return mask;
 }
 static bool use_ew12(int epi, int a_major) { return a_major == VMAE_MAJOR_K && ((ew12_mask() >> epi) & 1); }
@@ -523,6 +562,7 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
       const bool bmn = b_major == VMAE_MAJOR_MN;
       if (epi == EPI_BF16_GELU && !bmn) return launch_gemm<192, 0, 0, EPI_BF16_GELU, 12>(m, p, grid, stream);
       if (epi == EPI_BF16_DGELU) return bmn ? launch_gemm<192, 0, 1, EPI_BF16_DGELU, 12>(m, p, grid, stream) : launch_gemm<192, 0, 0, EPI_BF16_DGELU, 12>(m, p, grid, stream);
+      if (epi == EPI_BF16_DGELU_Q8) return bmn ? launch_gemm<192, 0, 1, EPI_BF16_DGELU_Q8, 12>(m, p, grid, stream) : launch_gemm<192, 0, 0, EPI_BF16_DGELU_Q8, 12>(m, p, grid, stream);
       if (epi == EPI_F32_RESID && !bmn) return launch_gemm<192, 0, 0, EPI_F32_RESID, 12>(m, p, grid, stream);
     }
   }
@@ -533,6 +573,10 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
     case EPI_F32: return dispatch_major<BLOCK_N, EPI_F32>(a_major, b_major, m, p, grid, stream);
     case EPI_F32_RESID: return dispatch_major<BLOCK_N, EPI_F32_RESID>(a_major, b_major, m, p, grid, stream);
     case EPI_BF16_NOISE: return launch_gemm<BLOCK_N, 0, 0, EPI_BF16_NOISE>(m, p, grid, stream);   // forward layout only
+    case EPI_BF16_GELU_Q8: return launch_gemm<BLOCK_N, 0, 0, EPI_BF16_GELU_Q8>(m, p, grid, stream);   // forward layout only
+    case EPI_BF16_DGELU_Q8:
+      if (a_major != VMAE_MAJOR_K) return fail(VMAE_ERR_UNSUPPORTED, "quantised gelu' input needs a K-major A operand");
+      return b_major == VMAE_MAJOR_MN ? launch_gemm<BLOCK_N, 0, 1, EPI_BF16_DGELU_Q8>(m, p, grid, stream) : launch_gemm<BLOCK_N, 0, 0, EPI_BF16_DGELU_Q8>(m, p, grid, stream);
     default:
       if constexpr (BLOCK_N <= 192) return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
       else return fail(VMAE_ERR_UNSUPPORTED, "accumulating GEMM with BLOCK_N=256 is not instantiated");
@@ -559,11 +603,11 @@ static int pick_block_n(int M, int N, int k_splits, bool accumulate, bool ew12) 
 }
 
 static int make_box_map(CUtensorMap* m, const void* base, int dtype, int M, int N, long long ld) {
-  const int es = dtype == VMAE_DTYPE_F32 ? 4 : 2;
+  const int es = dtype == VMAE_DTYPE_F32 ? 4 : (dtype == VMAE_DTYPE_U8 ? 1 : 2);
   const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
   const uint64_t str[1] = {(uint64_t)ld * es};
   const uint32_t box[2] = {32, 32};
-  return make_tmap(m, base, dtype, 2, dims, str, box, 32 * es);
+  return make_tmap(m, base, dtype, 2, dims, str, box, dtype == VMAE_DTYPE_U8 ? 0 : 32 * es);   // the 32-byte uint8 rows are not swizzled
 }
 
 }  // namespace vmae
@@ -585,9 +629,10 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
   VMAE_CHECK_ARG(!(a_major == VMAE_MAJOR_MN && b_major == VMAE_MAJOR_K), "vmae_gemm_bf16: (A MN-major, B K-major) is not instantiated");
   VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 || out_dtype == VMAE_DTYPE_F32, "vmae_gemm_bf16: bad out_dtype %d", out_dtype);
   VMAE_CHECK_ARG(!accumulate || out_dtype == VMAE_DTYPE_F32, "vmae_gemm_bf16: accumulate needs fp32 output");
-  VMAE_CHECK_ARG(act == VMAE_ACT_NONE || act == VMAE_ACT_GELU, "vmae_gemm_bf16: bad act %d", act);
+  VMAE_CHECK_ARG(act >= VMAE_ACT_NONE && act <= VMAE_ACT_AUX_Q8, "vmae_gemm_bf16: bad act %d", act);
   if (k_splits < 1) k_splits = 1;
   VMAE_CHECK_ARG(k_splits == 1 || accumulate, "vmae_gemm_bf16: split-K needs accumulate=1");
+  VMAE_CHECK_ARG(act != VMAE_ACT_AUX_Q8 || aux_in, "vmae_gemm_bf16: act=AUX_Q8 needs aux_in");
   VMAE_CHECK_ARG(!accumulate || (!bias && !residual && !aux_in && !aux_out && act == VMAE_ACT_NONE),
                  "vmae_gemm_bf16: accumulate supports only the plain epilogue");
   VMAE_CHECK_ARG(ld_out % (out_dtype == VMAE_DTYPE_F32 ? 4 : 8) == 0, "vmae_gemm_bf16: ld_out misaligned");
@@ -601,13 +646,16 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
     epi = EPI_BF16_NOISE;
   } else if (accumulate) {
     epi = EPI_F32_ACCUM;
-  } else if (act == VMAE_ACT_GELU) {
+  } else if (act == VMAE_ACT_GELU || act == VMAE_ACT_GELU_Q8) {
     VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && aux_out && !residual && !aux_in,
                    "vmae_gemm_bf16: act=GELU needs bf16 output with aux_out (pre-activation) and no residual/aux_in");
-    epi = EPI_BF16_GELU;
+    VMAE_CHECK_ARG(act == VMAE_ACT_GELU || (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K && ld_aux_out % 16 == 0),
+                   "vmae_gemm_bf16: GELU_Q8 needs the forward layout and ld_aux_out %% 16 == 0");
+    epi = act == VMAE_ACT_GELU ? EPI_BF16_GELU : EPI_BF16_GELU_Q8;
   } else if (aux_in) {
     VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_BF16 && !residual && !aux_out && !bias, "vmae_gemm_bf16: aux_in (gelu') needs a plain bf16 output");
-    epi = EPI_BF16_DGELU;
+    VMAE_CHECK_ARG(act == VMAE_ACT_NONE || (act == VMAE_ACT_AUX_Q8 && ld_aux_in % 16 == 0), "vmae_gemm_bf16: aux_in takes act NONE (bf16) or AUX_Q8 (uint8, ld %% 16 == 0)");
+    epi = act == VMAE_ACT_AUX_Q8 ? EPI_BF16_DGELU_Q8 : EPI_BF16_DGELU;
   } else if (residual) {
     VMAE_CHECK_ARG(out_dtype == VMAE_DTYPE_F32 && !aux_out, "vmae_gemm_bf16: residual needs fp32 output");
     epi = EPI_F32_RESID;
@@ -655,7 +703,9 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
   if (rc) return rc;
   maps.aux = maps.out;
   if (epi == EPI_BF16_GELU) rc = make_box_map(&maps.aux, aux_out, VMAE_DTYPE_BF16, M, N, ld_aux_out);
+  else if (epi == EPI_BF16_GELU_Q8) rc = make_box_map(&maps.aux, aux_out, VMAE_DTYPE_U8, M, N, ld_aux_out);
   else if (epi == EPI_BF16_DGELU) rc = make_box_map(&maps.aux, aux_in, VMAE_DTYPE_BF16, M, N, ld_aux_in);
+  else if (epi == EPI_BF16_DGELU_Q8) rc = make_box_map(&maps.aux, aux_in, VMAE_DTYPE_U8, M, N, ld_aux_in);
   else if (epi == EPI_F32_RESID) rc = make_box_map(&maps.aux, residual, VMAE_DTYPE_F32, M, N, ld_res);
   if (rc) return rc;
 

@@ -29,3 +29,19 @@ def visible_indices(mask):
             raise ValueError("visible_indices: clips keep different numbers of patches")
         rows.append(ids)
     return torch.stack(rows).to(torch.int32)
+
+
+def sample_frame_indices(total_frames: int, clip_len: int, stride: int, rng=None):
+    """Temporal window of `LazyVideoMAEDataset.__getitem__` (:44-59): `clip_len` frame indices. Videos shorter than
+    clip_len*stride frames are sampled uniformly (linspace, truncated to int); otherwise a random start (numpy's global RNG, as in
+    the reference, or `rng`) and a fixed stride. Always exactly clip_len indices. Host-side; the decoded uint8 frames then go to the
+    GPU as [B, T, H, W, 3] and `ops.frames_to_clip` does ToTensor + Normalize + the channel reversal + the [C, T, H, W] permute."""
+    import numpy as np
+
+    window = clip_len * stride
+    if total_frames < window:
+        idx = np.linspace(0, total_frames - 1, clip_len).astype(int)
+    else:
+        start = (rng or np.random).randint(0, total_frames - window + 1)
+        idx = np.arange(start, start + window, stride)
+    return idx[:clip_len]

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os as _os
 import weakref
 from typing import Optional
 
@@ -104,6 +105,12 @@ def gemm(a, b, M, N, K, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, resi
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     lib = L.load()
+    # the gelu' side tensor may be one byte per element (vmae.h: VMAE_ACT_GELU_Q8 / VMAE_ACT_AUX_Q8): selected by its dtype
+    if aux_out is not None and aux_out.dtype == torch.uint8:
+        assert act == L.ACT_GELU
+        act = L.ACT_GELU_Q8
+    if aux_in is not None and aux_in.dtype == torch.uint8:
+        act = L.ACT_AUX_Q8
     kind = "gemm_wgrad" if a_major == L.MAJOR_MN else ("gemm_dgrad" if b_major == L.MAJOR_MN else "gemm_fwd")
     rc = _run(kind, 2.0 * M * N * K, lambda: lib.vmae_gemm_bf16(
         _p(a), a.stride(0), a_major, _p(b), b.stride(0), b_major, M, N, K, _p(bias), _p(residual),
@@ -334,8 +341,9 @@ def attn_fwd(qkv, B, Lq, H, hd, p_drop=0.0, seed=0):
     return out, lse
 
 
+GELU_PRIME_Q8 = _os.environ.get("VMAE_GELU_Q8", "1") != "0"   # fused blocks save gelu' as uint8 (A/B switch)
 ATTN_BWD_FUSED = True   # single-pass backward (head_dim 64); False forces the two-kernel form
-ATTN_BWD_FUSED_MIN_L = 384
+ATTN_BWD_FUSED_MIN_L = int(_os.environ.get("VMAE_ATTN_FUSED_MIN_L", "128"))
 
 
 def attn_bwd(qkv, out, dout, lse, B, Lq, H, hd, p_drop=0.0, seed=0, fused=None):
@@ -716,7 +724,9 @@ class TransformerBlockFn(torch.autograd.Function):
         else:
             x1 = linear_fwd(o, wp, proj_b, residual=x)
         ln2, mean2, rstd2 = layernorm_fwd(x1, ln2_w, ln2_b)
-        h_pre = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
+        # gelu'(fc1 output), saved for backward: one byte per element (quantisation step 0.0049) unless the dropout path needs to
+        # rescale it in bf16 — the fc1 GEMM is bound by HBM write bandwidth and this is a quarter of what it writes
+        h_pre = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=torch.uint8 if (GELU_PRIME_Q8 and not drop and w1.shape[0] % 16 == 0) else BF16)
         act = linear_fwd(ln2, w1, fc1_b, act=L.ACT_GELU, aux_out=h_pre)
         if drop:   # same mask on the activation and on the saved gelu' (so backward needs no extra pass)
             dropout_apply(act, p_drop, s_act, out=act)

@@ -215,3 +215,20 @@ def test_stack2_restatement_matches_reference_mask_and_gather(stack2):
         loss.backward()
         for k, gref in case["grads"].items():
             assert torch.allclose(sd[k].grad, gref, rtol=2e-3, atol=1e-7 + 2e-4 * float(gref.abs().max())), (mode, k)
+
+
+def test_frame_window_sampling_matches_reference_semantics():
+    """mae_loader.py:44-59 restated: always clip_len indices; short videos -> truncated linspace; long videos -> random start + stride
+    drawn from numpy's global RNG exactly like the reference (same seed -> same window)."""
+    import numpy as np
+
+    from ssl_vit_video_analytics_b200.datasets.mae_loader import sample_frame_indices
+
+    assert list(sample_frame_indices(10, 16, 2)) == list(np.linspace(0, 9, 16).astype(int))
+    assert len(sample_frame_indices(1, 16, 2)) == 16 and set(sample_frame_indices(1, 16, 2)) == {0}
+    np.random.seed(5)
+    start = np.random.randint(0, 100 - 32 + 1)
+    np.random.seed(5)
+    got = sample_frame_indices(100, 16, 2)
+    assert list(got) == list(range(start, start + 32, 2)) and len(got) == 16
+    assert list(sample_frame_indices(32, 16, 2)) == list(range(0, 32, 2))

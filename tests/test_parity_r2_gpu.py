@@ -715,3 +715,30 @@ def test_tubelet_embed_implicit_gemm_fwd_and_grads(B, T, S, pt, ratio):
     assert torch.allclose(dev_args[4].grad.cpu(), dt_ref, rtol=1e-4, atol=1e-4 * float(dt_ref.abs().max()))
     ds_ref = torch.zeros(Lp, E).index_add_(0, vis.long()[:, None, :].expand(B, Tp, n_vis).reshape(-1), dy)
     assert torch.allclose(dev_args[5].grad.cpu().reshape(Lp, E), ds_ref, rtol=1e-4, atol=1e-4 * float(ds_ref.abs().max()) + 1e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1536, 384), (300, 192, 384), (1000, 1152, 384), (77, 576, 72)])
+def test_gemm_gelu_with_8bit_saved_derivative(M, N, K):
+    """VMAE_ACT_GELU_Q8 / VMAE_ACT_AUX_Q8: the activation is unchanged, gelu' comes back within half a quantisation step (0.0025),
+    and the dgrad epilogue multiplies by the dequantised value."""
+    from ssl_vit_video_analytics_b200 import _lib as L, ops
+
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.08).bfloat16()
+    b = torch.randn(N, device=DEV, generator=g)
+    q = torch.empty(M, N, device=DEV, dtype=torch.uint8)
+    d16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    y8 = ops.gemm(x, w, M, N, K, bias=b, act=L.ACT_GELU, aux_out=q)
+    y16 = ops.gemm(x, w, M, N, K, bias=b, act=L.ACT_GELU, aux_out=d16)
+    assert torch.equal(y8, y16)
+    pre = (x.float() @ w.float().t() + b).requires_grad_(True)
+    F.gelu(pre).sum().backward()
+    deq = q.float() * (1.26 / 255) - 0.13
+    assert float((deq - pre.grad).abs().max()) <= 0.0025 + 2e-4, float((deq - pre.grad).abs().max())
+    xk = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    out = ops.gemm(xk, w, M, N, K, aux_in=q)                                  # (xk W^T) * dequant(q)
+    ref = (xk.float() @ w.float().t()) * deq
+    assert float((out.float() - ref).abs().max()) <= 1.5e-2 * float(ref.abs().max())
+    out_mn = ops.linear_dgrad(xk, w.t().contiguous(), aux_in=q)               # MN-major B (the layout the dgrad of fc2 uses)
+    assert float((out_mn.float() - ref).abs().max()) <= 1.5e-2 * float(ref.abs().max())

@@ -1,5 +1,5 @@
 """Launch each hot kernel once at decoder-sized shapes (for `ncu --set full`): python tools/prof_kernels.py
-Round structure: the sequence below runs twice; profile the second round (skip = launches of one round)."""
+The sequence below runs twice; the second round sits in the NVTX range "prof": profile it with `ncu --nvtx --nvtx-include "prof/"`."""
 import sys
 from pathlib import Path
 
@@ -30,7 +30,20 @@ wparams = [torch.nn.Parameter(torch.randn(1536, 384, device=dev, generator=g)) f
 for p_ in wparams:
     p_.grad = torch.randn_like(p_) * 0.01
 adamw = FusedAdamW(wparams, lr=1e-4, weight_decay=0.05)
-for _ in range(2):
+from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices  # noqa: E402
+clip64 = torch.randn(64, 3, 16, 224, 224, device=dev, generator=g)
+vis64 = visible_indices(get_tube_mask(64, 8, 196, 0.9)).to(dev)
+we = (torch.randn(384, 3, 2, 16, 16, device=dev, generator=g) * 0.03)
+be = torch.zeros(384, device=dev)
+tpos, spos = torch.zeros(1, 8, 1, 384, device=dev), torch.zeros(1, 1, 196, 384, device=dev)
+x_enc = torch.randn(10240, D, device=dev, generator=g)
+for rnd in range(2):
+    if rnd == 1:
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("prof")
+    emb = ops.TubeletEmbedFn.apply(clip64, vis64, we.requires_grad_(True), be, tpos, spos, 2, 16)   # tubelet embed: implicit GEMM, TMA 5-D gather
+    emb.backward(torch.ones_like(emb))                                              # its implicit wgrad (+ colsum)
+    ops.LinearNoiseFn.apply(x_enc, wp.float(), bp, 0.1, 1, 0, None)                 # enc_to_dec with the feature-noise epilogue
     ops.gemm(x, w1, M, 1536, D, bias=b1)                                            # 1 qkv/pred-like: bias, bf16 out
     act = ops.gemm(x, w1, M, 1536, D, bias=b1, act=L.ACT_GELU, aux_out=pre)        # 2 fc1: bias + GELU + pre-activation
     ops.gemm(x, wp, M, D, D, bias=bp, residual=xf, out_dtype=torch.float32)       # 3 proj: bias + fp32 residual
@@ -45,4 +58,5 @@ for _ in range(2):
     ops.masked_mse(pred, clip, mask, 2, 16, 1)                                     # 13-14 loss (+ finalize)
     adamw.step()                                                                   # AdamW over 36 tensors in one launch (+ tick)
 torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
 print("done")
