@@ -452,7 +452,7 @@ def run_ours(args, cfg):
     barrier()
     copy_stream = torch.cuda.Stream(device=dev)
     bufs = [torch.empty_like(clip_d), torch.empty_like(clip_d)]
-    refresh_masks = args.workload == "vit_s"
+    refresh_masks = args.workload == "vit_s" and os.environ.get("VMAE_BENCH_STATIC_MASK", "0") != "1"
     if refresh_masks:
         from ssl_vit_video_analytics_b200.datasets.mae_loader import get_tube_mask, visible_indices
 
