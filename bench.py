@@ -338,6 +338,11 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: first touch then lands on the GPU's own NUMA node
     if world > 1:
+        # --nccl-channels N caps NCCL_MAX_NCHANNELS (A/B knob). Measured at 8 GPUs: default 17.80 ms/step, 4 channels 18.70, 2 channels
+        # 20.9 — the collective of the LAST bucket (it completes with the end of backward) is on the critical path, so a slower
+        # allreduce costs more than the SMs a faster one borrows from the persistent kernels. Default: NCCL's own choice.
+        if args.nccl_channels > 0:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
         dist.init_process_group("nccl", device_id=dev)
     use_graph = args.graph != "off"
     if use_graph:
@@ -376,7 +381,7 @@ def run_ours(args, cfg):
     else:
         B = PER_GPU_BATCH if args.batch is None else args.batch
         model = VideoMAEViT(cfg).to(dev).train()
-        ddp = GradientBucketer(model, bucket_mb=32.0, exclude=())
+        ddp = GradientBucketer(model, bucket_mb=args.bucket_mb, exclude=())
         clip_h, mask_h, vis_h = make_inputs(B, cfg, seed=rank)
         mask_d, vis_d = mask_h.to(dev), vis_h.to(dev)
         # every input buffer owns its (static) mask tensors: the e2e loop draws a fresh tube mask per step on the host, like
@@ -799,6 +804,8 @@ def run_fedavg(args, cfg):
         agg_ms += ea.elapsed_time(e1)
     barrier()
     total_ms = e0.elapsed_time(e1)
+    if not is_client:
+        agg_ms = 0.0   # an idle rank enters the allreduce at once and waits there for the clients' local steps: not aggregation time
     t = torch.tensor([total_ms, agg_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -845,6 +852,8 @@ def main():
     ap.add_argument("--allreduce", default="captured", choices=["captured", "between"],
                     help="N > 1 with graphs: captured = NCCL bucket allreduces inside the one captured step, overlapped with backward (default); "
                          "between = eager allreduces between a forward+backward graph and an AdamW graph")
+    ap.add_argument("--nccl-channels", type=int, default=0, help="cap NCCL_MAX_NCHANNELS (0 = NCCL's default; A/B knob)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient bucket size (the last bucket's allreduce is exposed: smaller = shorter tail, more launches)")
     ap.add_argument("--workload", default="vit_s", choices=["vit_s", "tinyvit", "fedavg"],
                     help="vit_s = BASELINE headline (default); tinyvit = the drop-in TinyVideoMAE at configs/ssl_mae.yaml shapes; "
                          "fedavg = BASELINE config 5 (5 clients across the GPUs, local steps + weighted-allreduce aggregation)")
