@@ -869,7 +869,7 @@ int att_trace_read_fused(long long* host) { return att_trace_read_tu(host); }
 
 // Returns 0 on success, <0 on error. dq_accum: fp32 [B, L, H*64] workspace (zeroed here).
 int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* dq_accum, int B, int L, int H,
-                        float scale, float p_drop, unsigned long long seed, cudaStream_t stream) {
+                        float scale, float p_drop, unsigned long long seed, cudaStream_t stream, bool accum_zeroed) {
   using namespace fb;
   CUtensorMap m_qkv, m_do, m_dq;
   {
@@ -901,7 +901,7 @@ int attn_bwd_fused_hd64(const void* qkv, const void* dout, const float* lse, con
   // opt-in: measured 867 -> 834 us at B=64 L=1568, but the dQ error (max-norm, vs fp32 reference) grows from 4.2e-3 to 1.2e-2 —
   // 13 bf16 additions per element. The default keeps the fp32 accumulator: parity before 4 %.
   static const bool dq_bf16 = [] { const char* e = getenv("VMAE_FB_DQ_BF16"); return e ? atoi(e) != 0 : false; }();
-  if (!(use_v2 && G == 2 && dq_bf16)) VMAE_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * L * H * HD * sizeof(float), stream));
+  if (!(use_v2 && G == 2 && dq_bf16) && !accum_zeroed) VMAE_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * L * H * HD * sizeof(float), stream));
   if (use_v2 && G == 2 && dq_bf16) {
     // bf16 reduction straight into the q slot of dqkv [B, L, 3, H, 64]: zero the slot (strided), no accumulator memset, no convert kernel
     CUtensorMap m_dqb;
