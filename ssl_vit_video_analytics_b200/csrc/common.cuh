@@ -72,6 +72,27 @@ inline cudaError_t launch_pdl(int group, void (*kernel)(KArgs...), dim3 grid, di
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Same, launched as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(int group, int cluster_x, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(group) ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = cluster_x;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Build a tiled TMA descriptor over a bf16 tensor. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
 // swizzle_bytes: 0, 64 or 128; the inner box extent in bytes must not exceed it.
 int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -152,7 +152,15 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float
 __device__ __forceinline__ uint32_t box_f32_slot(uint32_t box, int r, int j) { return box + r * 128 + ((j ^ (r & 7)) << 4); }
 __device__ __forceinline__ uint32_t box_bf16_slot(uint32_t box, int r, int j) { return box + r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
-template <int BLOCK_N, int A_MN, int B_MN, int EPI, int EW = GEMM_EPI_WARPS>
+// CL = 2: the kernel runs as CTA PAIRS (thread-block clusters of two). The two CTAs of a pair work on vertically adjacent tiles
+// (rows m0 and m0 + 128, same columns, same K range), so they need the SAME B tile: each loads one half of it and TMA multicast
+// delivers that half into both CTAs' shared memory. Everything else (A tile, UMMAs, TMEM accumulators, epilogue) stays per CTA.
+// Why: with 128 x 192 tiles one K block needs 40 KB of operands per 384 UMMA cycles = 107 B/clk/SM, 15.8 KB/clk over 148 SMs,
+// about twice what the L2 delivers to the SMs — which is why every tile shape sat at 50-60 % tensor-pipe activity no matter how deep
+// the operand ring was. Sharing B takes a pair's L2 reads from 80 to 56 KB per K block (-30 %).
+// The only cross-CTA state is the operand ring: a stage is refilled (by BOTH producers, each writing into both CTAs) only when both
+// CTAs' UMMAs have drained it, so empty barriers count two arrivals, one of them the peer's multicast commit.
+template <int BLOCK_N, int A_MN, int B_MN, int EPI, int EW = GEMM_EPI_WARPS, int CL = 1>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
@@ -177,7 +185,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  static_assert(CL == 1 || CL == 2, "single CTAs or CTA pairs");
+  const int cta_rank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_unit = static_cast<int>(blockIdx.x) / CL;     // persistent loop: a pair walks the (pair-)units together
+  const int unit_stride = static_cast<int>(gridDim.x) / CL;
+  const int m_tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M + CL - 1) / CL;   // CL == 2: pairs of row tiles (the last may hang over M)
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int kb_per_split = (num_kb + p.k_splits - 1) / p.k_splits;  // host guarantees: no split is empty
@@ -190,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (ET::HAS_IN || ET::DUAL) tma_prefetch_desc(&tma_aux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -214,6 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // the peer's barriers exist before any multicast load or commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel; from here on this grid reads
@@ -227,7 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int rest = unit / n_tiles;
     const int mt = rest % m_tiles;
     const int ks = rest / m_tiles;
-    m0 = mt * GEMM_BLOCK_M;
+    m0 = (mt * CL + cta_rank) * GEMM_BLOCK_M;
     n0 = nt * BLOCK_N;
     kb0 = ks * kb_per_split;
     kb1 = min(kb0 + kb_per_split, num_kb);
@@ -238,7 +251,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         int m0, n0, kb0, kb1;
         decode(unit, m0, n0, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -254,7 +267,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           } else {
             tma_load_2d(sa, &tma_a, full_bar(stage), k0, m0);
           }
-          if (B_MN) {
+          if (CL == 2) {
+            // this CTA fetches its half of the pair's B tile; multicast writes it into both CTAs and completes the bytes on both
+            // CTAs' full barriers (the peer's half arrives the same way: STAGE_BYTES land here in total)
+            if (B_MN) {
+              constexpr int NB = BLOCK_N / 64, NB0 = (NB + 1) / 2;   // 64-column boxes: rank 0 takes the first NB0
+              const int i0 = cta_rank == 0 ? 0 : NB0, i1 = cta_rank == 0 ? NB0 : NB;
+              for (int i = i0; i < i1; ++i)
+                tma_load_2d_multicast(sb + i * (GEMM_BLOCK_K * 128), &tma_b, full_bar(stage), n0 + i * 64, k0, 0x3);
+            } else {
+              tma_load_2d_multicast(sb + cta_rank * (BLOCK_N / 2) * 128, &tma_b, full_bar(stage), k0, n0 + cta_rank * (BLOCK_N / 2), 0x3);
+            }
+          } else if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 64; ++i)
               tma_load_2d(sb + i * (GEMM_BLOCK_K * 128), &tma_b, full_bar(stage), n0 + i * 64, k0);
@@ -285,7 +309,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         int m0, n0, kb0, kb1;
         decode(unit, m0, n0, kb0, kb1);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -307,7 +331,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               umma_bf16(tmem_base + 2 * BLOCK_N + as * 16, dA + k * A_STEP, dOnes + k * ((GEMM_UMMA_K * 2) >> 4), idesc_ones, acc);
             }
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these UMMAs retire
+          // smem slot reusable once these UMMAs retire (pairs: tell the peer's producer too — it writes half of B into this CTA)
+          if (CL == 2) umma_commit_multicast(empty_bar(stage), 0x3);
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
@@ -335,13 +361,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       gm = m0 + quad * 32;
       gn = n0 + half * COLS_PER_WARP + c * 32;
     };
-    if (ET::HAS_IN && lane == 0 && static_cast<int>(blockIdx.x) < total_units) {
+    if (ET::HAS_IN && lane == 0 && first_unit < total_units) {
       int gm, gn;
-      chunk_coords(blockIdx.x, 0, gm, gn);
+      chunk_coords(first_unit, 0, gm, gn);
       mbar_expect_tx(in_bar(ew, 0), ET::IN_BYTES);
       tma_load_2d(my_staging, &tma_aux, in_bar(ew, 0), gn, gm);
     }
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (EPI == EPI_F32_ACCUM && p.bias_grad != nullptr && half == 0) {
@@ -499,7 +525,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (ET::HAS_IN) {
             // prefetch the input box of the next item into the other buffer
             int nunit = unit, nc = c + 1;
-            if (nc == CHUNKS) { nunit = unit + gridDim.x; nc = 0; }
+            if (nc == CHUNKS) { nunit = unit + unit_stride; nc = 0; }
             if (nunit < total_units) {
               int ngm, ngn;
               chunk_coords(nunit, nc, ngm, ngn);
@@ -518,6 +544,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // no CTA retires while its peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -526,11 +553,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
 struct GemmMaps {
   CUtensorMap a, b, out, aux;
+  CUtensorMap b_half;   // CTA pairs, K-major B: the same tensor with a box of BLOCK_N / 2 rows
+  bool pairs;           // launch as CTA pairs (clusters of two) sharing the B tile by TMA multicast
 };
+
+// How many CTA pairs of this kernel can be resident at once (one CTA per SM, both SMs of a pair in one GPC: a GPC with an odd
+// number of free SMs leaves one out). Queried once per instantiation.
+template <typename K>
+static int max_resident_pairs(K kern, int threads, int smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = num_sms() / 2 - 4;   // conservative: never more pairs than could be co-resident
+  }
+  return n;
+}
 
 template <int BLOCK_N, int A_MN, int B_MN, int EPI, int EW = GEMM_EPI_WARPS>
 static int launch_gemm(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, EPI, EW>;
+  if (m.pairs) {
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, EW, 2>;
+    static thread_local int max_pairs = 0;
+    if (max_pairs == 0) {
+      VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      max_pairs = max_resident_pairs(kern, gemm_threads(EW), Cfg::SMEM_BYTES);
+    }
+    const int m_pairs = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M + 1) / 2;
+    const long long units = (long long)m_pairs * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.k_splits;
+    const int pairs = (int)(units < max_pairs ? units : max_pairs);
+    VMAE_CUDA(launch_pdl_cluster(PDL_GEMM, 2, kern, dim3(2 * pairs), dim3(gemm_threads(EW)), Cfg::SMEM_BYTES, stream, m.a, B_MN ? m.b : m.b_half, m.out, m.aux, p));
+    return VMAE_OK;
+  }
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, EW>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -699,6 +764,17 @@ static int gemm_impl(const void* A, long long lda, int a_major, const void* B, l
     rc = make_tmap_bf16(&maps.b, B, 2, dims, str, box, 128);
   }
   if (rc) return rc;
+  // CTA pairs (see the kernel's CL parameter): worth it when there are at least two row tiles per column tile to pair up
+  static const int pair_mode = [] { const char* e = getenv("VMAE_GEMM_PAIRS"); return e ? atoi(e) : 0; }();
+  maps.pairs = pair_mode != 0 && (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M >= 2;
+  maps.b_half = maps.b;
+  if (maps.pairs && b_major == VMAE_MAJOR_K) {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)ldb * 2};
+    const uint32_t box[2] = {64, (uint32_t)block_n / 2};
+    rc = make_tmap_bf16(&maps.b_half, B, 2, dims, str, box, 128);
+    if (rc) return rc;
+  }
   rc = make_box_map(&maps.out, out, out_dtype, M, N, ld_out);
   if (rc) return rc;
   maps.aux = maps.out;

@@ -209,6 +209,26 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 // mbarrier arrives once all previously issued UMMAs of this thread have completed (implies fence::before_thread_sync)
+// Thread-block clusters (used by the GEMM's CTA pairs): rank inside the cluster, the cluster-wide barrier, a TMA load that lands at the
+// same shared-memory offset in every CTA of `mask` (and completes bytes on the mbarrier at the same offset in each of them), and an
+// UMMA commit that arrives on the mbarrier at the same offset in every CTA of `mask`.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
