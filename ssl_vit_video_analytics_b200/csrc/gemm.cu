@@ -63,7 +63,10 @@ struct EpiTraits {
   static constexpr int IN_BYTES = (EPI == EPI_BF16_DGELU_Q8) ? 32 * 32 : 32 * 32 * (OUT_F32 ? 4 : 2);   // bytes of the epilogue-input box
   static constexpr int BOX_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);     // one 32x32 staging box
   static constexpr int BUF_BYTES = BOX_BYTES * (DUAL ? 2 : 1);     // per buffer (dual: activation + pre-activation)
-  static constexpr int WARP_BYTES = 2 * BUF_BYTES;                  // double buffered
+  // double buffered, except split-K accumulation: its epilogue runs once per long K range, and the 16 KB it gives back (with four
+  // epilogue warps) are a fifth operand stage — wgrad went from ~870 to ~1000 TF/s on the decoder shapes with the deeper ring
+  static constexpr int NBUF = (EPI == EPI_F32_ACCUM) ? 1 : 2;
+  static constexpr int WARP_BYTES = NBUF * BUF_BYTES;
   static constexpr int STAGING_BYTES = EW * WARP_BYTES;
 };
 
@@ -383,7 +386,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c, ++item) {
-        const int b = item & 1;
+        const int b = ET::NBUF == 2 ? (item & 1) : 0;
         const uint32_t buf = my_staging + b * ET::BUF_BYTES;
         int gm, gn;
         chunk_coords(unit, c, gm, gn);
@@ -521,7 +524,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           else tma_store_2d(&tma_out, buf, gn, gm);
           if (EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_Q8) tma_store_2d(&tma_aux, buf + ET::BOX_BYTES, gn, gm);
           tma_store_commit();
-          tma_store_wait_read<1>();  // the other buffer (previous item) has been read out -> free for reuse
+          tma_store_wait_read<ET::NBUF - 1>();  // the buffer the next item writes has been read out -> free for reuse
           if (ET::HAS_IN) {
             // prefetch the input box of the next item into the other buffer
             int nunit = unit, nc = c + 1;
@@ -606,11 +609,11 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int grid, cudaStr
   return VMAE_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int EW = GEMM_EPI_WARPS>
 static int dispatch_major(int a_major, int b_major, const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K) return launch_gemm<BLOCK_N, 0, 0, EPI>(m, p, grid, stream);
-  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_MN) return launch_gemm<BLOCK_N, 0, 1, EPI>(m, p, grid, stream);
-  return launch_gemm<BLOCK_N, 1, 1, EPI>(m, p, grid, stream);
+  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_K) return launch_gemm<BLOCK_N, 0, 0, EPI, EW>(m, p, grid, stream);
+  if (a_major == VMAE_MAJOR_K && b_major == VMAE_MAJOR_MN) return launch_gemm<BLOCK_N, 0, 1, EPI, EW>(m, p, grid, stream);
+  return launch_gemm<BLOCK_N, 1, 1, EPI, EW>(m, p, grid, stream);
 }
 
 // Epilogues that run with 12 epilogue warps on 192-wide tiles (bit mask over EPI ids; VMAE_GEMM_EW12 overrides for A/B runs)
@@ -643,7 +646,13 @@ static int dispatch_epi(int epi, int a_major, int b_major, const GemmMaps& m, co
       if (a_major != VMAE_MAJOR_K) return fail(VMAE_ERR_UNSUPPORTED, "quantised gelu' input needs a K-major A operand");
       return b_major == VMAE_MAJOR_MN ? launch_gemm<BLOCK_N, 0, 1, EPI_BF16_DGELU_Q8>(m, p, grid, stream) : launch_gemm<BLOCK_N, 0, 0, EPI_BF16_DGELU_Q8>(m, p, grid, stream);
     default:
-      if constexpr (BLOCK_N <= 192) return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
+      if constexpr (BLOCK_N <= 192) {
+        // split-K accumulation runs its epilogue once per long K range: four epilogue warps with single-buffered staging (16 KB
+        // instead of 64) leave room for five operand stages instead of three
+        static const bool ew4 = [] { const char* e = getenv("VMAE_GEMM_ACCUM_EW4"); return e ? atoi(e) != 0 : true; }();
+        if (ew4) return dispatch_major<BLOCK_N, EPI_F32_ACCUM, 4>(a_major, b_major, m, p, grid, stream);
+        return dispatch_major<BLOCK_N, EPI_F32_ACCUM>(a_major, b_major, m, p, grid, stream);
+      }
       else return fail(VMAE_ERR_UNSUPPORTED, "accumulating GEMM with BLOCK_N=256 is not instantiated");
   }
 }
