@@ -369,593 +369,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 }
 
 // ======================================================================================================================
-// forward v2 (round 2): ONE CTA per SM with TWO 128-row query tiles in explicit ping-pong.
-//
-// Measured on v1 (two independent CTAs per SM): a CTA's block takes ~3 000 cycles when a second CTA is co-resident and ~2 200 when it
-// has the SM alone (VMAE_ATT_FWD_1CTA experiment: 399 -> 587 us with half the CTAs), and 768 of those cycles are the 96 MUFU ex2 per
-// thread. The two co-resident CTAs drift into phase: their exponential phases collide on the sub-partition's single MUFU pipe (1 536
-// cycles for both instead of 768 each while the other does its loads / row maximum / TMEM stores). Here both tiles live in one
-// CTA — two row warpgroups (216 registers each), one UMMA-issuing warp per tile (a single in-order issuer would make one tile's ready
-// UMMAs wait behind the other tile's barrier), one shared K/V ring (each K/V tile is fetched once for 256 query rows) — and a token
-// (two mbarriers) is passed between the groups so that their exponential phases ALTERNATE: group 1 may start exp(j) when group 0 has
-// finished exp(j), group 0 may start exp(j+1) when group 1 has finished exp(j).
+// Forward variants that were built, validated against the fp32 reference and measured on (B, H, L, hd) = (64, 6, 1568, 64), then
+// removed because none beat the kernel above (392 us; cuDNN SDPA 358-364 us on the same box). Numbers, traces and the pipe
+// micro-benchmark behind them: profiles/r2_attn_fwd_experiments.txt, tools/microbench_sfu.cu, DESIGN.md section 5.
+//   * one CTA per SM, two 128-row query tiles in explicit ping-pong over a shared K/V ring, one UMMA-issuing warp per tile, the
+//     exponential phases alternated by a token (two mbarriers): 456 us (464 us without the token);
+//   * this kernel with the block's 128 key columns split over two row warpgroups (four row warps per sub-partition, shared row
+//     maximum through shared memory): 419 us;
+//   * both combined (640 threads, 104 registers per row thread): 488 us (500 us without the token).
+// What they showed: a sub-partition retires one MUFU.EX2 warp-instruction per 8 cycles and overlaps it fully with FFMA2 / FADD2 /
+// F2FP / FMNMX, but only with >= 2 warps inside the exponential loop; a lone warp runs the loop in 1 250-1 500 cycles per 128
+// columns against 768 of MUFU time, so strict alternation trades the MUFU collisions for the lone-warp inefficiency and loses the
+// second CTA's cover of prologue and epilogue. XU pipe 49 % busy, tensor pipe 32 %, issue slots 47 % (ncu) for the kernel above.
 // ======================================================================================================================
-template <int HD>
-struct Fwd2Cfg {
-  static constexpr int BKV = 128;
-  static constexpr int ROWB = HD * 2;
-  static constexpr int Q_BYTES = 128 * ROWB;
-  static constexpr int KV_BYTES = BKV * ROWB;
-  static constexpr int NS = 3;
-  static constexpr int OFF_Q = 0;                          // Q[2]
-  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;        // K[NS]
-  static constexpr int OFF_V = OFF_K + NS * KV_BYTES;      // V[NS]
-  static constexpr int OFF_BAR = OFF_V + NS * KV_BYTES;
-  static constexpr int OFF_XCH = OFF_BAR + 256;            // row maxima [tile 2][parity 2][half 2][128] fp32, then normalisers [tile 2][half 2][128] fp32
-  static constexpr int SMEM_BYTES = OFF_XCH + 4096 + 2048;
-  // warps 0-3 control (0 / 2: UMMA issuers of tile 0 / 1; 1: TMA), then per tile two row warpgroups (key columns [0,64) and [64,128))
-  static constexpr int THREADS = 128 + 512;
-  static constexpr int TILE_COLS = 256;                    // per tile: S fp32 [0,128) | O fp32 [128,128+HD) | P bf16 operand (64 packed columns)
-  static constexpr int CTRL_REGS = 40, ROW_REGS = 104;     // 640 threads x 96 at launch >= 128 x 40 + 512 x 104
-};
-
-template <int HD, bool DROP>
-__global__ void __launch_bounds__(Fwd2Cfg<HD>::THREADS, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale, const AttnDrop drop, int token_mode) {
-  using Cfg = Fwd2Cfg<HD>;
-  static_assert(128 * Cfg::CTRL_REGS + 512 * Cfg::ROW_REGS <= Cfg::THREADS * 96, "register pool");
-  constexpr int BKV = Cfg::BKV, NS = Cfg::NS;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  check_smem_alignment(smem_raw);
-  const uint32_t sbase = smem_u32(smem_raw);
-  auto sQ = [&](int g) { return sbase + Cfg::OFF_Q + g * Cfg::Q_BYTES; };
-  auto sK = [&](int s) { return sbase + Cfg::OFF_K + s * Cfg::KV_BYTES; };
-  auto sV = [&](int s) { return sbase + Cfg::OFF_V + s * Cfg::KV_BYTES; };
-  const uint32_t bar = sbase + Cfg::OFF_BAR;
-  const uint32_t q_full = bar;
-  auto kv_full = [&](int s) { return bar + 8 + 8 * s; };      // 8, 16, 24
-  auto kv_empty = [&](int s) { return bar + 32 + 8 * s; };    // 32, 40, 48   (one commit per tile's issuer)
-  auto s_full = [&](int g) { return bar + 56 + 8 * g; };      // 56, 64
-  auto s_free = [&](int g) { return bar + 72 + 8 * g; };      // 72, 80
-  auto p_ready = [&](int g) { return bar + 88 + 8 * g; };     // 88, 96
-  auto o_full = [&](int g) { return bar + 104 + 8 * g; };     // 104, 112
-  auto token = [&](int g) { return bar + 120 + 8 * g; };      // 120, 128: tile g may run its exponential phase
-  const uint32_t tmem_ptr_addr = bar + 144;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 144);
-  float* xch_max = reinterpret_cast<float*>(smem_raw + Cfg::OFF_XCH);
-  float* xch_l = reinterpret_cast<float*>(smem_raw + Cfg::OFF_XCH + 4096);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_base = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (L + BKV - 1) / BKV;
-  const bool two = q_base + 128 < L;   // the second tile holds real rows (false only for the last CTA of a sequence)
-  ATT_TRACE_INIT();
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), two ? 2 : 1); }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(s_full(g), 1);
-      mbar_init(s_free(g), 8);
-      mbar_init(p_ready(g), 8);
-      mbar_init(o_full(g), 1);
-      mbar_init(token(g), 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(tmem_ptr_addr, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_gen;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp < 4) {
-    setmaxnreg_dec<Cfg::CTRL_REGS>();
-    if (warp == 1 && elect_one()) {   // TMA producer
-      mbar_expect_tx(q_full, (two ? 2 : 1) * Cfg::Q_BYTES);
-      tma_load_3d(sQ(0), &map_q, q_full, h * HD, q_base, b);
-      if (two) tma_load_3d(sQ(1), &map_q, q_full, h * HD, q_base + 128, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % NS;
-        mbar_wait(kv_empty(s), ((j / NS) & 1) ^ 1u);
-        mbar_expect_tx(kv_full(s), 2 * Cfg::KV_BYTES);
-        tma_load_3d(sK(s), &map_kv, kv_full(s), (H + h) * HD, j * BKV, b);
-        tma_load_3d(sV(s), &map_kv, kv_full(s), (2 * H + h) * HD, j * BKV, b);
-      }
-    } else if ((warp == 0 || warp == 2) && elect_one()) {   // UMMA issuer of tile g
-      const int g = warp >> 1;
-      if (g == 0 || two) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-        const uint32_t tS = tmem + g * Cfg::TILE_COLS, tO = tS + BKV, tP = tS + BKV + HD;
-        const uint64_t dQ = umma_smem_desc(sQ(g), 0, 8 * Cfg::ROWB, Cfg::ROWB);
-        uint64_t dK[NS], dV[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          dK[s] = umma_smem_desc(sK(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
-          dV[s] = umma_smem_desc(sV(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
-        }
-        auto issue_s = [&](int j) {
-          const int s = j % NS;
-          mbar_wait(kv_full(s), (j / NS) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, dQ + 2 * k, dK[s] + 2 * k, idesc_s, k > 0);
-          umma_commit(s_full(g));
-        };
-        mbar_wait(q_full, 0);
-        issue_s(0);
-        for (int j = 0; j < nkv; ++j) {
-          const int s = j % NS;
-          if (g == 0) { ATT_STAMP(1, j, 0); }
-          if (j + 1 < nkv) {
-            mbar_wait(s_free(g), j & 1);
-            tc_fence_after();
-            issue_s(j + 1);
-          }
-          if (g == 0) { ATT_STAMP(1, j, 2); }
-          mbar_wait(p_ready(g), j & 1);
-          tc_fence_after();
-          if (g == 0) { ATT_STAMP(1, j, 3); }
-#pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk)
-            umma_bf16_ts(tO, tP + kk * 8, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
-          umma_commit(o_full(g));
-          umma_commit(kv_empty(s));
-          if (g == 0) { ATT_STAMP(1, j, 4); }
-        }
-      }
-    }
-  } else {
-    setmaxnreg_inc<Cfg::ROW_REGS>();
-    const int g = (warp - 4) >> 3;             // query tile
-    const int half = ((warp - 4) >> 2) & 1;    // which 64 of the block's 128 key columns, and which HD/2 columns of O
-    if (g == 0 || two) {
-      const int quad = warp & 3;
-      const int row = quad * 32 + lane;
-      const int col0 = half * 64;
-      constexpr int OC = HD / 2;
-      const int q0 = q_base + g * 128;
-      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t tS = tmem + g * Cfg::TILE_COLS, tO = tS + BKV, tP = tS + BKV + HD;
-      const float sl2 = scale * LOG2E;
-      const uint32_t drop_base = (static_cast<uint32_t>((b * H + h) * L + q0 + row)) * DROP_CQ + drop.seed_lo;
-      const int stamp_thread = 128;   // first row warp of tile 0
-      const bool pass_token = two && token_mode != 0;
-      float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < nkv; ++j) {
-        ATT_STAMP_T(0, j, 0, stamp_thread);
-        mbar_wait(s_full(g), j & 1);
-        tc_fence_after();
-        ATT_STAMP_T(0, j, 1, stamp_thread);
-        uint32_t sc[2][32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tmem_ld32(tS + lane_off + col0 + c * 32, sc[c]);
-        tmem_wait_ld();
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(s_free(g));
-        ATT_STAMP_T(0, j, 2, stamp_thread);
-        const int valid = min(BKV, L - j * BKV);
-        if (valid < BKV) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + c * 32 + i >= valid) sc[c][i] = 0xff800000u;
-        }
-        float mx2[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          mx2[c] = fmaxf(__uint_as_float(sc[c][0]), __uint_as_float(sc[c][1]));
-#pragma unroll
-          for (int i = 2; i < 32; i += 2) mx2[c] = fmax3(mx2[c], __uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1]));
-        }
-        // the row's maximum over both halves (slots alternate with the block parity: one barrier per block)
-        float* xm = xch_max + (g * 2 + (j & 1)) * 256;
-        const float own = fmaxf(mx2[0], mx2[1]);
-        xm[half * 128 + row] = own;
-        named_bar_sync(1 + g, 256);
-        const float mx = fmaxf(own, xm[(half ^ 1) * 128 + row]);
-        if (j == 0) {
-          m = mx;
-        } else {
-          const bool need = (mx - m) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {   // the same rows, hence the same decision, in both halves
-            mbar_wait(o_full(g), (j - 1) & 1);
-            tc_fence_after();
-            const float m_new = need ? mx : m;
-            const float alpha = ex2_approx((m - m_new) * sl2);
-            m = m_new;
-            l *= alpha;
-#pragma unroll
-            for (int oc = 0; oc < OC; oc += 16) {
-              uint32_t r[16];
-              tmem_ld16(tO + lane_off + half * OC + oc, r);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st16(tO + lane_off + half * OC + oc, r);
-            }
-            tmem_wait_st();
-          }
-        }
-        const float msl = m * sl2;
-        ATT_STAMP_T(0, j, 3, stamp_thread);
-        // ---- the token: the sub-partitions' MUFU pipes belong to one tile (two warps per sub-partition) at a time
-        if (pass_token) {
-          if (g == 0) { if (j > 0) mbar_wait(token(0), (j - 1) & 1); }
-          else mbar_wait(token(1), j & 1);
-        }
-        ATT_STAMP_T(0, j, 4, stamp_thread);
-        if (threadIdx.x == 384) { ATT_STAMP_T(1, j, 5, 384); }
-        f32x2 l2[2] = {0ull, 0ull};
-        const f32x2 sl2_2 = pk2(sl2), nmsl_2 = pk2(-msl);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const f32x2 x2 = fma2(pk2(__uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1])), sl2_2, nmsl_2);
-            f32x2 p2;
-            if ((((i >> 1) * FWD_POLY_PAIRS) & 15) < FWD_POLY_PAIRS) {
-              p2 = exp2_poly2(x2);
-            } else {
-              float a, b2;
-              up2(x2, a, b2);
-              p2 = pk2(ex2_approx(a), ex2_approx(b2));
-            }
-            l2[c] = add2(l2[c], p2);
-            float p0, p1;
-            up2(p2, p0, p1);
-            if (DROP) {
-              const uint32_t w = drop_mix32(drop_base + static_cast<uint32_t>((j * BKV + col0 + c * 32 + i) >> 1) * DROP_CK) ^ drop.seed_hi;
-              if ((w & 0xffffu) < drop.thr) p0 = 0.f;
-              if ((w >> 16) < drop.thr) p1 = 0.f;
-            }
-            sc[c][i >> 1] = pack_bf16x2(p0, p1);
-          }
-        }
-        if (pass_token) {   // hand the MUFU pipes to the other tile
-          __syncwarp();
-          if (lane == 0) mbar_arrive(token(g ^ 1));
-        }
-        if (threadIdx.x == 384) { ATT_STAMP_T(1, j, 6, 384); }
-        {
-          float a, b2;
-          up2(add2(l2[0], l2[1]), a, b2);
-          l += a + b2;
-        }
-        if (j > 0) {
-          mbar_wait(o_full(g), (j - 1) & 1);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tmem_st16(tP + lane_off + half * 32 + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sc[c][0]));
-        ATT_STAMP_T(0, j, 5, stamp_thread);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready(g));
-        ATT_STAMP_T(0, j, 6, stamp_thread);
-      }
-      // the row's normaliser is the sum of the two halves' partial sums (same reference maximum)
-      xch_l[(g * 2 + half) * 128 + row] = l;
-      named_bar_sync(1 + g, 256);
-      const float l_tot = l + xch_l[(g * 2 + (half ^ 1)) * 128 + row];
-      mbar_wait(o_full(g), (nkv - 1) & 1);
-      tc_fence_after();
-      const float inv_l = (DROP ? drop.rp : 1.0f) / l_tot;
-      const int q_row = q0 + row;
-      {
-        uint32_t r[OC];
-        if (OC == 32) tmem_ld32(tO + lane_off + half * OC, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        else tmem_ld16(tO + lane_off + half * OC, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-        tmem_wait_ld();
-        if (q_row < L) {
-          __nv_bfloat16* dst = out + (static_cast<long long>(b) * L + q_row) * (H * HD) + h * HD + half * OC;
-#pragma unroll
-          for (int i = 0; i < OC; i += 8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-            pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-            pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-            pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + i) = pk;
-          }
-        }
-      }
-      if (half == 0 && q_row < L) lse[(static_cast<long long>(b) * H + h) * L + q_row] = m * scale + __logf(l_tot);
-      tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
-}
-
-// ======================================================================================================================
-// forward, column-split rows: the v1 pipeline (two CTAs per SM, S_{j+1} computed under softmax_j, P handed to the PV UMMA through
-// TMEM) with TWO row warpgroups per CTA, each owning 64 of the block's 128 key columns, so that every sub-partition holds four row
-// warps (two per CTA) instead of two.
-//
-// Why (tools/microbench_sfu.cu, gpurun_out/trace_fwd*.log): one sub-partition retires a MUFU.EX2 warp-instruction every 8 cycles and
-// overlaps it perfectly with FFMA2 / FADD2 / F2FP / FMNMX (2 cycles each) — when it has >= 2 warps IN the exponential loop. A lone
-// warp runs the same loop at 1 250-1 500 cycles per 128-column block against 768 of MUFU time (dependent latencies, a MUFU-dense
-// tail in the compiler's schedule), and with one row warp per CTA the sub-partition sees "two warps in the loop" only while the two
-// CTAs' exponential phases coincide — after which both sit in their non-MUFU phases (wait S, TMEM loads, row maximum, TMEM stores,
-// ~860 cycles) together. Four shorter row warps per sub-partition keep the MUFU pipe fed across those phases.
-//
-// The two halves of a row share one reference maximum: each publishes its 64-column maximum (rounded to bf16, so that both sides
-// compute the identical max(bf16(own), bf16(other)) — the reference only has to be NEAR the maximum) through 512 bytes of shared
-// memory and two named-barrier syncs; each half rescales / normalises / stores its own HD/2 columns of O, and the two partial
-// normalisers are added once at the end.
-// ======================================================================================================================
-constexpr int ATT_SPLIT_THREADS = 384;   // warps 0-3 control, 4-7 rows x columns [0,64), 8-11 rows x columns [64,128)
-constexpr int ATT_SPLIT_CTRL_REGS = 40;
-constexpr int ATT_SPLIT_ROW_REGS = 96;   // 2 CTAs x 384 threads: 80 registers per thread at launch; 128 x 40 + 256 x 96 <= 384 x 80
-static_assert(128 * ATT_SPLIT_CTRL_REGS + 256 * ATT_SPLIT_ROW_REGS <= ATT_SPLIT_THREADS * 80, "per-CTA register pool");
-
-template <int HD>
-struct FwdSplitCfg {
-  using Base = FwdCfg<HD, 128>;
-  static constexpr int OFF_XCH = Base::OFF_BAR + 128;          // 2 halves x 128 rows x bf16 (row maximum), later 128 x fp32 (normaliser)
-  static constexpr int SMEM_BYTES = OFF_XCH + 512;
-  static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
-};
-
-template <int HD, bool DROP>
-__global__ void __launch_bounds__(ATT_SPLIT_THREADS, 2)
-attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int H, float scale, const AttnDrop drop) {
-  constexpr int BKV = 128;
-  using Cfg = FwdCfg<HD, BKV>;
-  using SCfg = FwdSplitCfg<HD>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  check_smem_alignment(smem_raw);
-  const uint32_t sbase = smem_u32(smem_raw);
-  constexpr int NS = Cfg::NS;
-  const uint32_t sQ = sbase + Cfg::OFF_Q;
-  auto sK = [&](int s) { return sbase + Cfg::OFF_K + s * Cfg::KV_BYTES; };
-  auto sV = [&](int s) { return sbase + Cfg::OFF_V + s * Cfg::KV_BYTES; };
-  const uint32_t bar = sbase + Cfg::OFF_BAR;
-  const uint32_t q_full = bar, s_full = bar + 8, p_ready = bar + 16, o_full = bar + 24, s_free = bar + 104;
-  auto kv_full = [&](int s) { return bar + 32 + 8 * s; };
-  auto kv_empty = [&](int s) { return bar + 64 + 8 * s; };
-  const uint32_t tmem_ptr_addr = bar + 96;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::OFF_BAR + 96);
-  __nv_bfloat16* xch_max = reinterpret_cast<__nv_bfloat16*>(smem_raw + SCfg::OFF_XCH);   // [2][128]
-  float* xch_l = reinterpret_cast<float*>(smem_raw + SCfg::OFF_XCH);                      // [128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (L + BKV - 1) / BKV;
-  ATT_TRACE_INIT();
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
-    mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 8);
-    mbar_init(s_free, 8);
-    mbar_init(o_full, 1);
-    for (int s = 0; s < NS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tS = tmem, tO = tmem + BKV, tP = tmem + BKV + HD;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp < 4) {
-    setmaxnreg_dec<ATT_SPLIT_CTRL_REGS>();
-    if (warp == 1 && elect_one()) {   // TMA producer
-      mbar_expect_tx(q_full, Cfg::Q_BYTES);
-      tma_load_3d(sQ, &map_q, q_full, h * HD, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % NS;
-        mbar_wait(kv_empty(s), ((j / NS) & 1) ^ 1u);
-        mbar_expect_tx(kv_full(s), 2 * Cfg::KV_BYTES);
-        tma_load_3d(sK(s), &map_kv, kv_full(s), (H + h) * HD, j * BKV, b);
-        tma_load_3d(sV(s), &map_kv, kv_full(s), (2 * H + h) * HD, j * BKV, b);
-      }
-    } else if (warp == 0 && elect_one()) {   // UMMA issuer (same schedule as v1)
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-      const uint64_t dQ = umma_smem_desc(sQ, 0, 8 * Cfg::ROWB, Cfg::ROWB);
-      uint64_t dK[NS], dV[NS];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        dK[s] = umma_smem_desc(sK(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
-        dV[s] = umma_smem_desc(sV(s), 0, 8 * Cfg::ROWB, Cfg::ROWB);
-      }
-      auto issue_s = [&](int j) {
-        const int s = j % NS;
-        mbar_wait(kv_full(s), (j / NS) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, dQ + 2 * k, dK[s] + 2 * k, idesc_s, k > 0);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % NS;
-        ATT_STAMP(1, j, 0);
-        if (j + 1 < nkv) {
-          mbar_wait(s_free, j & 1);
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        ATT_STAMP(1, j, 2);
-        mbar_wait(p_ready, j & 1);
-        tc_fence_after();
-        ATT_STAMP(1, j, 3);
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16_ts(tO, tP + kk * 8, dV[s] + (kk * 16 * Cfg::ROWB) / 16, idesc_o, (j > 0 || kk > 0));
-        umma_commit(o_full);
-        umma_commit(kv_empty(s));
-        ATT_STAMP(1, j, 4);
-      }
-    }
-  } else {
-    setmaxnreg_inc<ATT_SPLIT_ROW_REGS>();
-    const int half = (warp - 4) >> 2;          // which 64 of the block's 128 key columns, and which HD/2 columns of O
-    const int quad = warp & 3;                 // TMEM lane quadrant of this warp
-    const int row = quad * 32 + lane;
-    const int col0 = half * 64;
-    constexpr int OC = HD / 2;                 // O columns per half
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const float sl2 = scale * LOG2E;
-    const uint32_t drop_base = (static_cast<uint32_t>((b * H + h) * L + q0 + row)) * DROP_CQ + drop.seed_lo;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      ATT_STAMP(0, j, 0);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      ATT_STAMP(0, j, 1);
-      uint32_t sc[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld32(tS + lane_off + col0 + c * 32, sc[c]);
-      tmem_wait_ld();
-      tc_fence_before();
-      if (lane == 0) mbar_arrive(s_free);
-      ATT_STAMP(0, j, 2);
-      const int valid = min(BKV, L - j * BKV);
-      if (valid < BKV) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + c * 32 + i >= valid) sc[c][i] = 0xff800000u;   // -inf
-      }
-      float mx2[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        mx2[c] = fmaxf(__uint_as_float(sc[c][0]), __uint_as_float(sc[c][1]));
-#pragma unroll
-        for (int i = 2; i < 32; i += 2) mx2[c] = fmax3(mx2[c], __uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1]));
-      }
-      // shared reference maximum of the row: both halves see the same two bf16 values (-inf survives the rounding)
-      const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx2[0], mx2[1]));
-      xch_max[half * 128 + row] = own;
-      named_bar_sync(1, 256);
-      const float mx = fmaxf(__bfloat162float(own), __bfloat162float(xch_max[(half ^ 1) * 128 + row]));
-      named_bar_sync(1, 256);   // the slot is rewritten in the next block
-      if (j == 0) {
-        m = mx;
-      } else {
-        const bool need = (mx - m) * sl2 > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {   // the same rows, hence the same decision, in both halves
-          mbar_wait(o_full, (j - 1) & 1);
-          tc_fence_after();
-          const float m_new = need ? mx : m;
-          const float alpha = ex2_approx((m - m_new) * sl2);
-          m = m_new;
-          l *= alpha;
-#pragma unroll
-          for (int oc = 0; oc < OC; oc += 16) {   // 16 columns at a time: the 64 scores stay in registers next to it
-            uint32_t r[16];
-            tmem_ld16(tO + lane_off + half * OC + oc, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(tO + lane_off + half * OC + oc, r);
-          }
-          tmem_wait_st();
-        }
-      }
-      const float msl = m * sl2;
-      ATT_STAMP(0, j, 3);
-      ATT_STAMP(0, j, 4);
-      f32x2 l2[2] = {0ull, 0ull};
-      const f32x2 sl2_2 = pk2(sl2), nmsl_2 = pk2(-msl);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const f32x2 x2 = fma2(pk2(__uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1])), sl2_2, nmsl_2);
-          f32x2 p2;
-          if ((((i >> 1) * FWD_POLY_PAIRS) & 15) < FWD_POLY_PAIRS) {
-            p2 = exp2_poly2(x2);
-          } else {
-            float a, b2;
-            up2(x2, a, b2);
-            p2 = pk2(ex2_approx(a), ex2_approx(b2));
-          }
-          l2[c] = add2(l2[c], p2);
-          float p0, p1;
-          up2(p2, p0, p1);
-          if (DROP) {
-            const uint32_t w = drop_mix32(drop_base + static_cast<uint32_t>((j * BKV + col0 + c * 32 + i) >> 1) * DROP_CK) ^ drop.seed_hi;
-            if ((w & 0xffffu) < drop.thr) p0 = 0.f;
-            if ((w >> 16) < drop.thr) p1 = 0.f;
-          }
-          sc[c][i >> 1] = pack_bf16x2(p0, p1);
-        }
-      }
-      {
-        float a, b2;
-        up2(add2(l2[0], l2[1]), a, b2);
-        l += a + b2;
-      }
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_st16(tP + lane_off + half * 32 + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sc[c][0]));
-      ATT_STAMP(0, j, 5);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-      ATT_STAMP(0, j, 6);
-    }
-    // the row's normaliser is the sum of the two halves' partial sums (same reference maximum)
-    if (half == 1) xch_l[row] = l;
-    named_bar_sync(1, 256);
-    const float l_other1 = xch_l[row];
-    named_bar_sync(1, 256);
-    if (half == 0) xch_l[row] = l;
-    named_bar_sync(1, 256);
-    const float l_tot = l + (half == 0 ? l_other1 : xch_l[row]);
-    mbar_wait(o_full, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = (DROP ? drop.rp : 1.0f) / l_tot;
-    const int q_row = q0 + row;
-    {
-      uint32_t r[OC];
-      if (OC == 32) tmem_ld32(tO + lane_off + half * OC, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      else tmem_ld16(tO + lane_off + half * OC, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_wait_ld();
-      if (q_row < L) {
-        __nv_bfloat16* dst = out + (static_cast<long long>(b) * L + q_row) * (H * HD) + h * HD + half * OC;
-#pragma unroll
-        for (int i = 0; i < OC; i += 8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-          pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-          pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-          pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + i) = pk;
-        }
-      }
-    }
-    if (half == 0 && q_row < L) lse[(static_cast<long long>(b) * H + h) * L + q_row] = m * scale + __logf(l_tot);
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, Cfg::TMEM_COLS); }
-}
 
 // ======================================================================================================================
 // backward: delta = rowsum(dO * O), then one templated kernel in two modes.
@@ -1320,39 +746,6 @@ static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   rc = make_map_rows(&mkv, qkv, B, L, 3 * H * HD, HD, BKV);
   if (rc) return rc;
   const AttnDrop drop = make_drop(p_drop, seed);
-  static const bool use_v2 = [] { const char* e = getenv("VMAE_ATT_FWD_V2"); return e ? atoi(e) != 0 : false; }();
-  static const bool use_split = [] { const char* e = getenv("VMAE_ATT_FWD_SPLIT"); return e ? atoi(e) != 0 : false; }();
-  if (use_split && L > 128) {   // column-split rows: four row warps per sub-partition (a single block leaves nothing to overlap)
-    using SC = FwdSplitCfg<HD>;
-    dim3 grid3((L + 127) / 128, H, B);
-    if (drop.thr > 0) {
-      auto kern = attn_fwd_split_kernel<HD, true>;
-      VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES));
-      VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid3, dim3(ATT_SPLIT_THREADS), SC::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
-    } else {
-      auto kern = attn_fwd_split_kernel<HD, false>;
-      VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES));
-      VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid3, dim3(ATT_SPLIT_THREADS), SC::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
-    }
-    VMAE_LAUNCH_CHECK();
-    return VMAE_OK;
-  }
-  static const int token_mode = [] { const char* e = getenv("VMAE_ATT_FWD_TOKEN"); return e ? atoi(e) : 1; }();
-  if (use_v2 && L > 128) {   // ping-pong kernel: 256 query rows per CTA (a single 128-row tile gains nothing from it)
-    using C2 = Fwd2Cfg<HD>;
-    dim3 grid2((L + 255) / 256, H, B);
-    if (drop.thr > 0) {
-      auto kern = attn_fwd2_kernel<HD, true>;
-      VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
-      VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid2, dim3(C2::THREADS), C2::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop, token_mode));
-    } else {
-      auto kern = attn_fwd2_kernel<HD, false>;
-      VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
-      VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid2, dim3(C2::THREADS), C2::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop, token_mode));
-    }
-    VMAE_LAUNCH_CHECK();
-    return VMAE_OK;
-  }
   dim3 grid((L + 127) / 128, H, B);
   if (drop.thr > 0) {
     auto kern = attn_fwd_kernel<HD, BKV, true>;
@@ -1360,11 +753,8 @@ static int launch_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
     VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
   } else {
     auto kern = attn_fwd_kernel<HD, BKV, false>;
-    // developer experiment: VMAE_ATT_FWD_1CTA=1 pads the dynamic shared memory so that only ONE CTA fits an SM (how much does a CTA
-    // speed up without a co-resident CTA competing for the MUFU pipe?)
-    static const int pad = [] { const char* e = getenv("VMAE_ATT_FWD_1CTA"); return (e && atoi(e)) ? 100 * 1024 : 0; }();
-    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES + pad));
-    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES + pad, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
+    VMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VMAE_CUDA(launch_pdl(PDL_ATTN, kern, grid, dim3(ATT_FWD_THREADS), Cfg::SMEM_BYTES, stream, mq, mkv, (__nv_bfloat16*)out, lse, L, H, scale, drop));
   }
   VMAE_LAUNCH_CHECK();
   return VMAE_OK;
