@@ -566,3 +566,18 @@ def test_fused_adamw_matches_torch_adamw(env):
         p = torch.nn.Parameter(torch.zeros(4))
         p.grad = torch.zeros(4)
         FusedAdamW([p]).step()
+
+
+@pytest.mark.gpu
+def test_gemm_cta_pairs_with_multicast_b_tile(env):
+    """VMAE_GEMM_PAIRS=1 launches every GEMM as clusters of two CTAs that share the B tile by TMA multicast (csrc/gemm.cu, CL = 2).
+    The switch is read once per process, so the three operand layouts and all epilogues run in a child process."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    child_env = dict(os.environ, VMAE_GEMM_PAIRS="1")
+    r = subprocess.run([sys.executable, str(root / "tools" / "dev_check_gemm.py"), "all"], env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mode all: ALL OK" in r.stdout and "BAD" not in r.stdout

@@ -144,6 +144,7 @@ def mode_perf():
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "kk"
     t0 = time.time()
-    ok = {"kk": mode_kk, "kmn": mode_kmn, "mnmn": mode_mnmn, "perf": mode_perf}[mode]()
+    ok = {"kk": mode_kk, "kmn": mode_kmn, "mnmn": mode_mnmn, "perf": mode_perf,
+          "all": lambda: mode_kk() & mode_kmn() & mode_mnmn()}[mode]()
     print(f"mode {mode}: {'ALL OK' if ok else 'FAILURES'} ({time.time()-t0:.1f}s)")
     sys.exit(0 if ok else 1)
