@@ -257,14 +257,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       // row maximum over the 128 scores with 3-input FMNMX3 (sm_100): 64 instead of 127 instructions on the half-rate ALU pipe,
       // four independent chains
-      float mx4[4];
+      // eight independent chains: with four, the 16-deep dependent FMNMX3 chains (~6 cycles each) made this phase latency-bound
+      float mx8[8];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        mx4[c] = fmaxf(__uint_as_float(sc[c][0]), __uint_as_float(sc[c][1]));
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) mx4[c] = fmax3(mx4[c], __uint_as_float(sc[c][i]), __uint_as_float(sc[c][i + 1]));
+        for (int hh = 0; hh < 2; ++hh) {
+          float v = fmaxf(__uint_as_float(sc[c][16 * hh]), __uint_as_float(sc[c][16 * hh + 1]));
+#pragma unroll
+          for (int i = 2; i < 16; i += 2) v = fmax3(v, __uint_as_float(sc[c][16 * hh + i]), __uint_as_float(sc[c][16 * hh + i + 1]));
+          mx8[2 * c + hh] = v;
+        }
       }
-      const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+      const float mx = fmax3(fmax3(mx8[0], mx8[1], mx8[2]), fmax3(mx8[3], mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
       if (j == 0) {
         m = mx;
       } else {
@@ -376,7 +381,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 //     exponential phases alternated by a token (two mbarriers): 456 us (464 us without the token);
 //   * this kernel with the block's 128 key columns split over two row warpgroups (four row warps per sub-partition, shared row
 //     maximum through shared memory): 419 us;
-//   * both combined (640 threads, 104 registers per row thread): 488 us (500 us without the token).
+//   * both combined (640 threads, 104 registers per row thread): 488 us (500 us without the token);
+//   * one CTA per SM, eight row warps of 64 columns with two score register sets per thread (block j+1's TMEM load and row maximum
+//     issued under block j's exponentials, independent per-half maxima / normalisers / O accumulators merged once at the end):
+//     612 us — the exponentials did overlap the next block's maximum (1 200 cycles for both), but ~750 cycles per block of barrier
+//     round trips (a satisfied mbarrier try_wait still costs ~150-200 cycles), TMEM store and hand-off stayed serial with no second
+//     CTA on the SM to cover them.
 // What they showed: a sub-partition retires one MUFU.EX2 warp-instruction per 8 cycles and overlaps it fully with FFMA2 / FADD2 /
 // F2FP / FMNMX, but only with >= 2 warps inside the exponential loop; a lone warp runs the loop in 1 250-1 500 cycles per 128
 // columns against 768 of MUFU time, so strict alternation trades the MUFU collisions for the lone-warp inefficiency and loses the
