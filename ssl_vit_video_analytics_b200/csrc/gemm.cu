@@ -458,16 +458,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             if (EPI == EPI_BF16_GELU_Q8) {
               // gelu' in [-0.129, 1.129] -> one byte: q = rn((g + 0.13) * 255 / 1.26); the box is 32 rows x 32 bytes, unswizzled
+              // Rounding by magic addend (adding 1.5 * 2^23 rounds to the integer grid and leaves it in the low mantissa byte; packed FMA + add per pair) and three
+              // byte permutes per word instead of clamp + F2I + shift + or per element: gelu' is bounded by [-0.1290, 1.1290]
+              // analytically (and the polynomial's argument is clamped), so q stays inside [0, 255] without a clamp.
               uint32_t q[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float t = fminf(fmaxf(fmaf(d[4 * j + k], 202.38095f, 26.309524f), 0.f), 255.f);
-                  w |= static_cast<uint32_t>(__float2int_rn(t)) << (8 * k);
-                }
-                q[j] = w;
+                float t0, t1, t2, t3;
+                up2(add2(fma2(pk2(d[4 * j], d[4 * j + 1]), pk2(202.38095f), pk2(26.309524f)), pk2(12582912.f)), t0, t1);
+                up2(add2(fma2(pk2(d[4 * j + 2], d[4 * j + 3]), pk2(202.38095f), pk2(26.309524f)), pk2(12582912.f)), t2, t3);
+                const uint32_t lo = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0040);
+                const uint32_t hi = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0040);
+                q[j] = __byte_perm(lo, hi, 0x5410);
               }
               sts_u4(buf + ET::BOX_BYTES + r * 32, q[0], q[1], q[2], q[3]);
               sts_u4(buf + ET::BOX_BYTES + r * 32 + 16, q[4], q[5], q[6], q[7]);
@@ -488,11 +490,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint4 qa = lds_u4(buf + r * 32), qb = lds_u4(buf + r * 32 + 16);
           __syncwarp();   // every lane has read its bytes before any lane's (larger) output row overwrites the region
           const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          // byte -> float without I2F: the byte becomes the low mantissa byte of 2^23 (one permute), minus 2^23 is exact
           float h[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) h[4 * j + k] = fmaf(static_cast<float>((qw[j] >> (8 * k)) & 0xffu), 0.0049411765f, -0.13f);
+          for (int j = 0; j < 8; ++j) {
+            const f32x2 a2 = pk2(__uint_as_float(__byte_perm(qw[j], 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(qw[j], 0x4B000000u, 0x7541)));
+            const f32x2 b2 = pk2(__uint_as_float(__byte_perm(qw[j], 0x4B000000u, 0x7542)), __uint_as_float(__byte_perm(qw[j], 0x4B000000u, 0x7543)));
+            up2(fma2(add2(a2, pk2(-8388608.f)), pk2(0.0049411765f), pk2(-0.13f)), h[4 * j], h[4 * j + 1]);
+            up2(fma2(add2(b2, pk2(-8388608.f)), pk2(0.0049411765f), pk2(-0.13f)), h[4 * j + 2], h[4 * j + 3]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts_u4(box_bf16_slot(buf, r, j), pack2(v[8 * j] * h[8 * j], v[8 * j + 1] * h[8 * j + 1]), pack2(v[8 * j + 2] * h[8 * j + 2], v[8 * j + 3] * h[8 * j + 3]),
