@@ -385,8 +385,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 //   * one CTA per SM, eight row warps of 64 columns with two score register sets per thread (block j+1's TMEM load and row maximum
 //     issued under block j's exponentials, independent per-half maxima / normalisers / O accumulators merged once at the end):
 //     612 us — the exponentials did overlap the next block's maximum (1 200 cycles for both), but ~750 cycles per block of barrier
-//     round trips (a satisfied mbarrier try_wait still costs ~150-200 cycles), TMEM store and hand-off stayed serial with no second
-//     CTA on the SM to cover them.
+//     round trips (54 cycles each even when already satisfied, tools/microbench_mbar.cu), TMEM load issue, P store and hand-off
+//     stayed serial, with no second CTA on the SM to cover them.
 // What they showed: a sub-partition retires one MUFU.EX2 warp-instruction per 8 cycles and overlaps it fully with FFMA2 / FADD2 /
 // F2FP / FMNMX, but only with >= 2 warps inside the exponential loop; a lone warp runs the loop in 1 250-1 500 cycles per 128
 // columns against 768 of MUFU time, so strict alternation trades the MUFU collisions for the lone-warp inefficiency and loses the
