@@ -386,7 +386,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 //     issued under block j's exponentials, independent per-half maxima / normalisers / O accumulators merged once at the end):
 //     612 us — the exponentials did overlap the next block's maximum (1 200 cycles for both), but ~750 cycles per block of barrier
 //     round trips (54 cycles each even when already satisfied, tools/microbench_mbar.cu), TMEM load issue, P store and hand-off
-//     stayed serial, with no second CTA on the SM to cover them.
+//     stayed serial, with no second CTA on the SM to cover them;
+//   * the same pipelining inside the two-CTA layout: 64-column K/V blocks (a thread holds two blocks of scores in 216 registers), S
+//     issued two blocks ahead, P double-buffered in TMEM so that the row warps wait for one barrier per block: 445 us (head_dim 32,
+//     L = 196: 333 vs 301 us). Twice as many blocks means twice the per-block hand-offs, and S = Q K^T with N = 64 runs at the 48-cycle
+//     shared-memory-read floor instead of 32 (tools/microbench_umma.cu). A lesson kept from it: an mbarrier's single parity bit cannot
+//     name a phase two completions back, so a consumer that skips waits may only wait for phase n after it KNOWS phase n-1 completed.
 // What they showed: a sub-partition retires one MUFU.EX2 warp-instruction per 8 cycles and overlaps it fully with FFMA2 / FADD2 /
 // F2FP / FMNMX, but only with >= 2 warps inside the exponential loop; a lone warp runs the loop in 1 250-1 500 cycles per 128
 // columns against 768 of MUFU time, so strict alternation trades the MUFU collisions for the lone-warp inefficiency and loses the
