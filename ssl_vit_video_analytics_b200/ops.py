@@ -428,6 +428,7 @@ class LinearFn(torch.autograd.Function):
         ctx.in_shape = shp
         ctx.in_dtype = x.dtype
         ctx.w_shape = weight.shape
+        ctx.params = (weight, bias)   # the Parameter objects: direct gradient accumulation (enable_direct_grad) needs their .grad
         return y.reshape(*shp[:-1], n_out)
 
     @staticmethod
@@ -438,12 +439,25 @@ class LinearFn(torch.autograd.Function):
             dy2 = gelu_bwd(dy2, pre)
         dx = linear_dgrad(dy2, wb) if ctx.needs_input_grad[0] else None
         dw = db = None
-        if ctx.needs_input_grad[1] and ctx.has_bias and ctx.needs_input_grad[2]:
-            dw, db = linear_wgrad_bias(dy2, x2)
-        elif ctx.needs_input_grad[1]:
-            dw = linear_wgrad(dy2, x2)
-        elif ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2)
+        need_w = ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        weight, bias = ctx.params
+        # accumulate straight into .grad where the owner of the buffers opted in: no zero-filled temporary, no "grad += new" pass
+        t_w = _direct_grad(weight) if need_w else None
+        t_b = _direct_grad(bias) if need_b else None
+        if need_w and need_b and (t_w is None) == (t_b is None):
+            dw, db = linear_wgrad_bias(dy2, x2, None if t_w is None else t_w.view(t_w.shape[0], -1), t_b)
+        else:
+            if need_w:
+                dw = linear_wgrad(dy2, x2, None if t_w is None else t_w.view(t_w.shape[0], -1))
+            if need_b:
+                db = colsum(dy2, t_b)
+        if t_b is not None:
+            db = None
+            _grad_done(bias)
+        if t_w is not None:
+            dw = None
+            _grad_done(weight)
         if dw is not None:
             dw = dw.reshape(ctx.w_shape)
         if dx is not None:
@@ -577,6 +591,7 @@ class LayerNormFn(torch.autograd.Function):
         ctx.save_for_backward(x2, g, mean, rstd)
         ctx.in_shape = shp
         ctx.in_dtype = x.dtype
+        ctx.params = (weight, bias)
         return y.reshape(shp)
 
     @staticmethod
@@ -584,7 +599,16 @@ class LayerNormFn(torch.autograd.Function):
         x2, g, mean, rstd = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         want_b = ctx.in_dtype == BF16
-        dx, dxb, dg, db = layernorm_bwd(dy2, x2, g, mean, rstd, want_bf16=want_b, want_f32=not want_b)
+        weight, bias = ctx.params
+        t_g = _direct_grad(weight) if ctx.needs_input_grad[1] else None
+        t_b = _direct_grad(bias) if ctx.needs_input_grad[2] else None
+        if t_g is None or t_b is None:   # the kernel writes both or neither in place
+            t_g = t_b = None
+        dx, dxb, dg, db = layernorm_bwd(dy2, x2, g, mean, rstd, dgamma=t_g, dbeta=t_b, want_bf16=want_b, want_f32=not want_b)
+        if t_g is not None:
+            dg = db = None
+            _grad_done(bias)
+            _grad_done(weight)
         dxo = dxb if want_b else dx
         return dxo.reshape(ctx.in_shape), dg, db, None, None
 
@@ -636,7 +660,7 @@ def _shadow_key(t):
     return (t.data_ptr(), t.numel())
 
 # Direct gradient accumulation (opt-in). For a parameter marked by `enable_direct_grad(params, hook)` that already owns a contiguous
-# fp32 .grad (e.g. a view into a GradientBucketer bucket) the fused block accumulates into it in place (TMA reduce-add / red.add)
+# fp32 .grad (e.g. a view into a GradientBucketer bucket) the fused block, LinearFn and LayerNormFn accumulate into it in place (TMA reduce-add / red.add)
 # and returns None to autograd: no zero-filled temporary, no extra "grad += new" pass. Because autograd then never sees that
 # gradient, tensor hooks do not fire and `torch.autograd.grad(...)` would get None — hence opt-in, by whoever owns the .grad
 # buffers and calls `.backward()`. `hook(param)` (per parameter, not one global) replaces the post-accumulate hook autograd
