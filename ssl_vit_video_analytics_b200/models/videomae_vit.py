@@ -15,7 +15,6 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import _lib as L
 from .. import ops
 from .mae_vit_adapter import DecoderLayer, DecoderStack, trunc_normal_
 from .tiny_vit import Attention, Mlp

@@ -149,8 +149,6 @@ def test_videomae_vit_full_size_properties():
         pred_p = model(clip_d[perm].contiguous(), mask_d[perm].contiguous())
     assert torch.equal(pred_p, pred[perm])
     # (2) masked pixels are invisible to the model: changing them changes no prediction
-    from oracle.restatement import patchify
-
     clip2 = clip.clone()
     B, C, T, H, W = clip.shape
     tok_mask = mask.reshape(B, 8, 14, 14)

@@ -3,7 +3,6 @@ usage: python tools/sass_opcodes.py > profiles/r2_sass_opcodes.txt
   UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UTMAREDG = TMA load/store/reduce, HMMA = legacy mma.sync (must be 0)."""
 import re
 import subprocess
-import sys
 from collections import OrderedDict
 from pathlib import Path
 
