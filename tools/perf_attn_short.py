@@ -1,4 +1,4 @@
-"""Developer probe (GPU): the encoder-shape attention of the benchmark (B=64, H=6, L=157 visible tokens, head_dim 64): forward, both
+"""Developer probe (GPU): the encoder-shape attention of the benchmark (B=64, H=6, L=160 visible tokens, head_dim 64): forward, both
 backward forms and torch SDPA (cuDNN) side by side. usage: python tools/perf_attn_short.py [L]"""
 import sys
 from pathlib import Path
@@ -9,7 +9,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ssl_vit_video_analytics_b200 import ops  # noqa: E402
 
 B, H, hd = 64, 6, 64
-L = int(sys.argv[1]) if len(sys.argv) > 1 else 157
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 qkv = torch.randn(B, L, 3, H, hd, device="cuda").bfloat16()
 flat = qkv.view(B * L, -1)
 o, lse = ops.attn_fwd(flat, B, L, H, hd)
