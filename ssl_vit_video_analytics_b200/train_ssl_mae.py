@@ -46,6 +46,8 @@ def train_one_epoch(model, loader, optimizer, scaler, epoch, device, config, wri
     total_loss = 0.0
     for step, clip in enumerate(loader):
         clip = clip.to(device, non_blocking=True)
+        if clip.dtype == torch.uint8:   # LazyVideoMAEDataset(uint8_frames=True): [B, T, H, W, 3] frames, normalised on the GPU
+            clip = ops.frames_to_clip(clip)
         B, Cc, T, H, W = clip.shape
         Lp = (H // 8) * (W // 8)
         mask = get_tube_mask(B, T, Lp, ssl_cfg["mask_ratio"]).to(device)
